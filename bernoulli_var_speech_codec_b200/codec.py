@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference's codec facade, running on libbvc (CUDA, sm_100a).
+
+Mirrors reference ``bvrnn_codec_model.py:19-76`` (``BVRNNCodecModel``: same constructor
+arguments, ``encode`` / ``decode`` / ``forward`` signatures, tensor conventions and error
+behaviour) and keeps the inner operators callable with the reference's signatures:
+``model.bvrnn.encode(y, varBitrate, h)`` / ``.decode(z, h)`` (bvrnn.py:163,211),
+``model.vocoder(mel, length)`` (third_party/BigVGAN/models.py:207) and
+``mel_spectrogram(...)`` (third_party/BigVGAN/meldataset.py:60).
+
+PyTorch is used for checkpoint unpickling, device memory and streams only; all arithmetic
+runs in libbvc.so through the C ABI of ``include/bvc.h``.  There is no CPU implementation:
+CPU tensors are copied to the handle's GPU, processed there and copied back
+(``bvc_encode_host`` / ``bvc_decode_host``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import tomllib
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .melbasis import slaney_mel_basis
+
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+default_config = os.path.join(root, "configs", "config_varBitRate.toml")
+default_chkpt_bvrnn = os.path.join(root, "chkpts", "bvrnn_var_bitrate_step200000")
+default_chkpt_vocoder = os.path.join(root, "chkpts", "bigvgan_causal_tiny_ftbvrnn_g_step3500000")
+
+SCALING = 10 ** (-10 / 20)   # reference bvrnn_codec_model.py:17
+
+
+class AttrDict(dict):
+    """dict with attribute access (reference third_party/BigVGAN/env.py:8-11)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.__dict__ = self
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _Engine:
+    """Owns one bvc_handle (one per model instance and device)."""
+
+    def __init__(self, conf: dict, device: torch.device):
+        self.lib = _lib.load()
+        if self.lib.bvc_abi_version() != 1:
+            raise RuntimeError("libbvc ABI version mismatch")
+        v = conf["vocoder_config"]
+        if v.get("activation", "snakebeta") != "snakebeta" or not v.get("snake_logscale", True):
+            raise NotImplementedError("only the shipped log-scale snakebeta activation is implemented")
+        for key in ("layers_sym", "layers_antialias"):
+            if any(v.get(key, [])):
+                raise NotImplementedError(f"vocoder_config.{key}=true is not implemented (shipped configs use false)")
+        for key in ("pre_sym", "post_sym", "antialias_post"):
+            if v.get(key, False):
+                raise NotImplementedError(f"vocoder_config.{key}=true is not implemented (shipped configs use false)")
+        if str(v.get("resblock", "1")) != "1":
+            raise ValueError("Wrong resblock")
+        dil = v["resblock_dilation_sizes"]
+        if any(list(d) != list(dil[0]) for d in dil) or len(dil[0]) != 3:
+            raise NotImplementedError("resblock_dilation_sizes must be the same 3 dilations for every kernel size")
+        if conf["winsize"] != 1024:
+            raise NotImplementedError("winsize must be 1024")
+        cfg = _lib.BvcConfig()
+        cfg.device = device.index
+        cfg.x_dim, cfg.h_dim, cfg.z_dim = conf["num_mels"], conf["h_dim"], conf["z_dim"]
+        cfg.var_bit = int(bool(conf["var_bit"]))
+        cfg.n_fft, cfg.hop, cfg.pad_left = conf["winsize"], conf["hopsize"], conf["mel_pad_left"]
+        cfg.voc_initial_channel = v["upsample_initial_channel"]
+        cfg.voc_num_stages = len(v["upsample_rates"])
+        if cfg.voc_num_stages != 4 or len(v["resblock_kernel_sizes"]) != 3:
+            raise NotImplementedError("vocoder must have 4 upsampling stages and 3 resblock kernel sizes")
+        cfg.voc_up_rates = (C.c_int32 * 4)(*v["upsample_rates"])
+        cfg.voc_up_kernels = (C.c_int32 * 4)(*v["upsample_kernel_sizes"])
+        cfg.voc_num_kernels = 3
+        cfg.voc_res_kernels = (C.c_int32 * 3)(*v["resblock_kernel_sizes"])
+        cfg.voc_res_dilations = (C.c_int32 * 3)(*dil[0])
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.bvc_create(C.byref(self.handle), C.byref(cfg)), "bvc_create")
+        self.device = device
+        self.conf = conf
+        self.X, self.H, self.Z = cfg.x_dim, cfg.h_dim, cfg.z_dim
+        self.hop = cfg.hop
+        # front-end constant tables (meldataset.py:67-70)
+        window = torch.hann_window(conf["winsize"], periodic=True, dtype=torch.float32).contiguous()
+        basis = np.ascontiguousarray(slaney_mel_basis(conf["fs"], conf["winsize"], conf["num_mels"],
+                                                      conf["fmin"], conf["fmax"]), dtype=np.float32)
+        _lib.check(self.lib.bvc_set_frontend(self.handle, _ptr(window), C.c_void_p(basis.ctypes.data)),
+                   "bvc_set_frontend")
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.bvc_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _load(self, fn, state_dict, what):
+        keep, arr = [], (_lib.BvcTensor * len(state_dict))()
+        for i, (name, t) in enumerate(state_dict.items()):
+            if not isinstance(t, torch.Tensor):
+                raise RuntimeError(f"{what}: state_dict entry {name!r} is not a tensor")
+            t = t.detach().to("cpu", torch.float32).contiguous()
+            if t.dim() == 0:
+                t = t.reshape(1)
+            if t.dim() > 4:
+                raise RuntimeError(f"{what}: unexpected rank for {name}")
+            keep.append(t)
+            arr[i].name = name.encode()
+            arr[i].data = t.data_ptr()
+            arr[i].ndim = t.dim()
+            for d in range(t.dim()):
+                arr[i].shape[d] = t.shape[d]
+        _lib.check(fn(self.handle, arr, len(state_dict)), what)
+
+    def load_bvrnn(self, sd):
+        self._load(self.lib.bvc_load_bvrnn, sd, "load_state_dict(vrnn)")
+
+    def load_vocoder(self, sd):
+        self._load(self.lib.bvc_load_vocoder, sd, "load_state_dict(generator)")
+
+    # ---- device entry points -------------------------------------------------
+    def _dev(self, t, name):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.device != self.device:
+            raise RuntimeError(f"{name} is on {t.device}, the codec runs on {self.device}")
+        return t.to(torch.float32).contiguous()
+
+    def logmel(self, x, scale):
+        x = self._dev(x, "x")
+        B, L = x.shape
+        mel = torch.empty(B, L // self.hop, self.X, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bvc_logmel(self.handle, _ptr(x), B, L, scale, _ptr(mel), _stream(self.device)),
+                       "mel_spectrogram")
+        return mel
+
+    def encode(self, mel, bits, bits_scalar, h0, want_logits=False, want_all_h=True, want_packed=False):
+        mel = self._dev(mel, "y")
+        B, T, _ = mel.shape
+        dev = self.device
+        codes = torch.empty(B, T, self.Z, device=dev, dtype=torch.float32)
+        all_h = torch.empty(B, T, self.H, device=dev, dtype=torch.float32) if want_all_h else None
+        logits = torch.empty(B, T, self.Z, device=dev, dtype=torch.float32) if want_logits else None
+        packed = torch.empty(B, T, device=dev, dtype=torch.int64) if want_packed else None
+        h_fin = torch.empty(B, self.H, device=dev, dtype=torch.float32)
+        bits_t = self._dev(bits, "varBitrate") if bits is not None else None
+        h0_t = self._dev(h0, "h") if h0 is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.bvc_encode(self.handle, _ptr(mel), _ptr(bits_t), float(bits_scalar), _ptr(h0_t), B, T,
+                                           _ptr(codes), _ptr(packed), _ptr(logits), _ptr(all_h), _ptr(h_fin),
+                                           _stream(dev)), "BVRNN.encode")
+        return codes, all_h, h_fin, logits, packed
+
+    def decode_mel(self, codes, h0):
+        codes = self._dev(codes, "z")
+        B, T, _ = codes.shape
+        mel = torch.empty(B, T, self.X, device=self.device, dtype=torch.float32)
+        h_fin = torch.empty(B, self.H, device=self.device, dtype=torch.float32)
+        h0_t = self._dev(h0, "h") if h0 is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bvc_decode_mel(self.handle, _ptr(codes), _ptr(h0_t), B, T, _ptr(mel), _ptr(h_fin),
+                                               _stream(self.device)), "BVRNN.decode")
+        return mel, h_fin
+
+    def vocode(self, mel_cl, length, inv_scale_div):
+        mel_cl = self._dev(mel_cl, "mel")
+        B, T, _ = mel_cl.shape
+        n = min(int(length), int(self.lib.bvc_vocoder_out_len(self.handle, T)))
+        wav = torch.empty(B, max(n, 0), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bvc_vocode(self.handle, _ptr(mel_cl), B, T, int(length), float(inv_scale_div),
+                                           _ptr(wav), _stream(self.device)), "BigVGAN.forward")
+        return wav
+
+    # ---- host entry points (H2D + compute + D2H inside the call) ---------------
+    def encode_host(self, x, scale, bits_scalar):
+        x = x.to(torch.float32).contiguous()
+        B, L = x.shape
+        codes = torch.empty(B, L // self.hop, self.Z, dtype=torch.float32, pin_memory=True)
+        _lib.check(self.lib.bvc_encode_host(self.handle, _ptr(x), B, L, scale, float(bits_scalar), _ptr(codes)),
+                   "encode")
+        return codes
+
+    def decode_host(self, codes, length, inv_scale_div):
+        codes = codes.to(torch.float32).contiguous()
+        B, T, _ = codes.shape
+        n = min(int(length), int(self.lib.bvc_vocoder_out_len(self.handle, T)))
+        wav = torch.empty(B, max(n, 0), dtype=torch.float32, pin_memory=True)
+        _lib.check(self.lib.bvc_decode_host(self.handle, _ptr(codes), B, T, int(length), float(inv_scale_div),
+                                            _ptr(wav)), "decode")
+        return wav
+
+    def debug_read(self, name, shape):
+        out = torch.empty(*shape, dtype=torch.float32)
+        _lib.check(self.lib.bvc_debug_read(self.handle, name.encode(), _ptr(out), out.numel()), "debug_read")
+        return out
+
+    def kernel_launches(self):
+        return int(self.lib.bvc_kernel_launches(self.handle))
+
+    def set_precision(self, mode):
+        _lib.check(self.lib.bvc_set_precision(self.handle, int(mode)), "set_precision")
+
+
+class _BVRNN(nn.Module):
+    """Operator-level mirror of reference ``BVRNN`` inference entry points (bvrnn.py:163,211)."""
+
+    def __init__(self, engine, h_dim, z_dim, x_dim, var_bit):
+        super().__init__()
+        self._engine = engine
+        self.h_dim, self.z_dim, self.x_dim, self.varBit = h_dim, z_dim, x_dim, var_bit
+
+    def encode(self, y, varBitrate, h):
+        """y (B,T,x_dim), varBitrate (B,T) bits per frame, h (1,B,h_dim) -> (z (B,T,z_dim), all_h (B,T,h_dim))."""
+        h0 = h[-1] if h is not None else None
+        codes, all_h, _, _, _ = self._engine.encode(y, varBitrate, 0.0, h0)
+        return codes, all_h
+
+    def decode(self, z, h):
+        """z (B,T,z_dim), h (1,B,h_dim) -> (mel (B,T,x_dim), h (1,B,h_dim))."""
+        mel, h_fin = self._engine.decode_mel(z, h[-1] if h is not None else None)
+        return mel, h_fin[None]
+
+
+class _Vocoder(nn.Module):
+    """Mirror of reference ``BigVGAN.forward(x, length)`` (third_party/BigVGAN/models.py:207-238)."""
+
+    def __init__(self, engine, h):
+        super().__init__()
+        self._engine = engine
+        self.h = h
+
+    def forward(self, x, length):
+        """x (B, num_mels, T) -> (B, 1, min(length, 256 T + 294))."""
+        return self._engine.vocode(x.permute(0, 2, 1), length, 1.0)[:, None, :]
+
+
+class BVRNNCodecModel(nn.Module):
+    def __init__(self, config_path=default_config, bvrnn_chkpt_path=default_chkpt_bvrnn,
+                 vocoder_chkpt_path=default_chkpt_vocoder, *, device=None):
+        '''
+        config_path: path to the toml config file
+        bvrnn_chkpt_path: path to the checkpoint of the BVRNN model
+        vocoder_chkpt_path: path to the checkpoint of the vocoder model
+        device (keyword-only extension): CUDA device the codec runs on (default: current CUDA device)
+        '''
+        super().__init__()
+        with open(config_path, "rb") as fh:
+            conf = tomllib.load(fh)
+        self.conf = conf
+        if not torch.cuda.is_available():
+            raise RuntimeError("BVRNNCodecModel (b200) needs a CUDA sm_100 device: there is no CPU path")
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("BVRNNCodecModel (b200) runs on CUDA devices only")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self._engine = _Engine(conf, device)
+
+        bvrnn_chkpt = torch.load(bvrnn_chkpt_path, map_location=torch.device('cpu'), weights_only=True)
+        vocoder_chkpt = torch.load(vocoder_chkpt_path, map_location=torch.device('cpu'), weights_only=True)
+        self._engine.load_bvrnn(bvrnn_chkpt['vrnn'])
+        self._engine.load_vocoder(vocoder_chkpt['generator'])
+
+        self.bvrnn = _BVRNN(self._engine, conf['h_dim'], conf['z_dim'], conf['num_mels'], bool(conf['var_bit']))
+        self.vocoder = _Vocoder(self._engine, AttrDict(conf['vocoder_config']))
+
+    @property
+    def device(self):
+        return self._engine.device
+
+    def bits_per_frame(self, bitrate):
+        return float(np.round(bitrate * self.conf['hopsize'] / self.conf['fs']))   # reference :58
+
+    def encode(self, x, bitrate):
+        '''
+        x: input waveform, shape (batch, length)
+        bitrate: target bitrate in bits per second, will be rounded to the nearest valid bitrate
+        '''
+        bits = self.bits_per_frame(bitrate)
+        if x.device.type == "cpu":
+            return self._engine.encode_host(x, SCALING, bits)
+        mel = self._engine.logmel(x, SCALING)
+        codes, _, _, _, _ = self._engine.encode(mel, None, bits, None, want_all_h=False)
+        return codes
+
+    def decode(self, codes, length):
+        '''
+        codes: latent binary codes, shape (batch, frames, z_dim)
+        length: length of the output waveform
+        '''
+        if codes.device.type == "cpu":
+            return self._engine.decode_host(codes, length, SCALING)
+        mel, _ = self._engine.decode_mel(codes, None)
+        return self._engine.vocode(mel, length, SCALING)
+
+    def forward(self, x, bitrate):
+        length = x.shape[1]
+        codes = self.encode(x, bitrate)
+        return self.decode(codes, length)
+
+    # ---- taps used by the parity tests (not part of the reference API) ----
+    def encode_with_taps(self, x, bitrate, h0=None, mel=None):
+        """Returns dict(mel, codes, logits, all_h, h_final, packed) for a CUDA input."""
+        if mel is None:
+            mel = self._engine.logmel(x, SCALING)
+        codes, all_h, h_fin, logits, packed = self._engine.encode(
+            mel, None, self.bits_per_frame(bitrate), h0, want_logits=True, want_all_h=True, want_packed=True)
+        return dict(mel=mel, codes=codes, logits=logits, all_h=all_h, h_final=h_fin, packed=packed)
+
+
+def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, padding_left,
+                    center=False, return_stft=False, *, _engine_cache={}):
+    """Mirror of reference third_party/BigVGAN/meldataset.py:60 for CUDA inputs: (B, L) -> (B, num_mels, T)."""
+    if center or return_stft:
+        raise NotImplementedError("center=True / return_stft=True are not on the codec path")
+    if y.device.type != "cuda":
+        raise RuntimeError("mel_spectrogram (b200) needs a CUDA tensor")
+    key = (y.device, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, padding_left)
+    eng = _engine_cache.get(key)
+    if eng is None:
+        if win_size != n_fft:
+            raise NotImplementedError("win_size must equal n_fft")
+        conf = dict(num_mels=num_mels, h_dim=1024, z_dim=64, var_bit=True, fs=sampling_rate, winsize=n_fft,
+                    hopsize=hop_size, mel_pad_left=padding_left if padding_left != -1 else (n_fft - hop_size) // 2,
+                    fmin=fmin, fmax=fmax,
+                    vocoder_config=dict(upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
+                                        upsample_initial_channel=128, resblock_kernel_sizes=[3, 7, 11],
+                                        resblock_dilation_sizes=[[1, 3, 5]] * 3, resblock="1"))
+        eng = _engine_cache[key] = _Engine(conf, y.device)
+    return eng.logmel(y, 1.0).permute(0, 2, 1)

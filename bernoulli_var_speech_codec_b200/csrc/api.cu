@@ -1,0 +1,654 @@
+// C ABI of libbvc.so (see include/bvc.h): handle, strict checkpoint loading and weight
+// preparation (weight-norm fold, concatenations, split-bf16 packing), workspace, entry points.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bvc {
+
+static thread_local std::string g_error;
+thread_local int64_t* g_launch_counter = nullptr;
+void set_error(const std::string& msg) { g_error = msg; }
+
+}  // namespace bvc
+
+using namespace bvc;
+
+struct bvc_handle {
+    bvc_config cfg;
+    BvrnnWeights bw;
+    VocoderWeights vw;
+    FrontendTables ft;
+    VocoderBuffers vb;
+    bool have_bvrnn = false, have_voc = false, have_frontend = false;
+    Workspace ws;
+    int64_t launches = 0;
+    int precision = 0;
+    std::vector<void*> allocs;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+struct HostTensor {
+    const float* data;
+    std::vector<int64_t> shape;
+    size_t numel() const {
+        size_t n = 1;
+        for (auto s : shape) n *= (size_t)s;
+        return n;
+    }
+};
+typedef std::map<std::string, HostTensor> TensorMap;
+
+struct Guard {   // selects the device and the launch counter for the duration of a call
+    int prev = -1;
+    bool ok = true;
+    explicit Guard(bvc_handle* h) {
+        cudaGetDevice(&prev);
+        if (cudaSetDevice(h->cfg.device) != cudaSuccess) { ok = false; set_error("cudaSetDevice failed"); }
+        g_launch_counter = &h->launches;
+    }
+    ~Guard() {
+        g_launch_counter = nullptr;
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+T* dev_upload(bvc_handle* h, const std::vector<T>& v) {
+    T* p = nullptr;
+    if (cudaMalloc(&p, v.size() * sizeof(T) + 16) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    h->allocs.push_back(p);
+    return p;
+}
+
+uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+float bf2f(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+bool make_linear(bvc_handle* h, const std::vector<float>& w, int N, int K, LinearWeights* out) {
+    out->N = N;
+    out->K = K;
+    out->w = dev_upload(h, w);
+    if (!out->w) return false;
+    if (K % 2 == 0) {
+        std::vector<uint32_t> hi((size_t)N * K / 2), lo((size_t)N * K / 2);
+        for (size_t i = 0; i < hi.size(); ++i) {
+            const float a = w[2 * i], b = w[2 * i + 1];
+            const uint16_t ah = f2bf(a), bh = f2bf(b);
+            const uint16_t al = f2bf(a - bf2f(ah)), bl = f2bf(b - bf2f(bh));
+            hi[i] = (uint32_t)ah | ((uint32_t)bh << 16);
+            lo[i] = (uint32_t)al | ((uint32_t)bl << 16);
+        }
+        out->w_hi = dev_upload(h, hi);
+        out->w_lo = dev_upload(h, lo);
+        if (!out->w_hi || !out->w_lo) return false;
+    }
+    return true;
+}
+
+int collect(const bvc_tensor* tensors, int n, TensorMap* m) {
+    for (int i = 0; i < n; ++i) {
+        const bvc_tensor& t = tensors[i];
+        if (!t.name || !t.data || t.ndim < 1 || t.ndim > 4) {
+            set_error("malformed tensor descriptor at index " + std::to_string(i));
+            return BVC_ERR_SCHEMA;
+        }
+        HostTensor ht;
+        ht.data = t.data;
+        ht.shape.assign(t.shape, t.shape + t.ndim);
+        if (!m->emplace(t.name, ht).second) {
+            set_error(std::string("duplicate tensor: ") + t.name);
+            return BVC_ERR_SCHEMA;
+        }
+    }
+    return BVC_OK;
+}
+
+// strict: every expected tensor present with the right shape, nothing extra
+int check_schema(const TensorMap& m, const std::vector<std::pair<std::string, std::vector<int64_t>>>& expect) {
+    for (auto& e : expect) {
+        auto it = m.find(e.first);
+        if (it == m.end()) {
+            set_error("missing key in state_dict: " + e.first);
+            return BVC_ERR_SCHEMA;
+        }
+        if (it->second.shape != e.second) {
+            std::string s = "size mismatch for " + e.first + ": got [";
+            for (auto d : it->second.shape) s += std::to_string(d) + ",";
+            s += "] expected [";
+            for (auto d : e.second) s += std::to_string(d) + ",";
+            set_error(s + "]");
+            return BVC_ERR_SCHEMA;
+        }
+    }
+    if (m.size() != expect.size()) {
+        for (auto& kv : m) {
+            bool found = false;
+            for (auto& e : expect) found = found || e.first == kv.first;
+            if (!found) {
+                set_error("unexpected key in state_dict: " + kv.first);
+                return BVC_ERR_SCHEMA;
+            }
+        }
+    }
+    return BVC_OK;
+}
+
+std::vector<float> to_vec(const HostTensor& t) { return std::vector<float>(t.data, t.data + t.numel()); }
+
+// rows [r0, r1) x cols [c0, c1) of a row-major [R, C] matrix
+std::vector<float> slice(const HostTensor& t, int64_t r0, int64_t r1, int64_t c0, int64_t c1) {
+    const int64_t C = t.shape[1];
+    std::vector<float> out((size_t)(r1 - r0) * (c1 - c0));
+    for (int64_t r = r0; r < r1; ++r)
+        memcpy(&out[(size_t)(r - r0) * (c1 - c0)], t.data + r * C + c0, sizeof(float) * (c1 - c0));
+    return out;
+}
+void append(std::vector<float>& a, const std::vector<float>& b) { a.insert(a.end(), b.begin(), b.end()); }
+
+// w = v * (g / ||v||), norm over all dims but 0 (old-style torch weight_norm, dim=0)
+std::vector<float> fold_weight_norm(const HostTensor& g, const HostTensor& v) {
+    const int64_t d0 = v.shape[0];
+    const size_t inner = v.numel() / (size_t)d0;
+    std::vector<float> w(v.numel());
+    for (int64_t i = 0; i < d0; ++i) {
+        double ss = 0.0;
+        for (size_t j = 0; j < inner; ++j) ss += (double)v.data[i * inner + j] * v.data[i * inner + j];
+        const float scale = g.data[i] / (float)sqrt(ss);
+        for (size_t j = 0; j < inner; ++j) w[i * inner + j] = v.data[i * inner + j] * scale;
+    }
+    return w;
+}
+
+int ensure_workspace(bvc_handle* h, size_t floats) {
+    const size_t bytes = floats * sizeof(float) + 4096;
+    if (h->ws.bytes < bytes) {
+        if (h->ws.base) {
+            cudaDeviceSynchronize();
+            cudaFree(h->ws.base);
+            h->ws.base = nullptr;
+            h->ws.bytes = 0;
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("workspace allocation of " + std::to_string(bytes >> 20) + " MiB failed");
+            return BVC_ERR_NOMEM;
+        }
+        h->ws.base = (float*)p;
+        h->ws.bytes = bytes;
+    }
+    h->ws.used = 0;
+    return BVC_OK;
+}
+
+#define REQUIRE(cond, code, msg)      \
+    do {                              \
+        if (!(cond)) {                \
+            set_error(msg);           \
+            return code;              \
+        }                             \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int bvc_abi_version(void) { return BVC_ABI_VERSION; }
+const char* bvc_last_error(void) { return g_error.c_str(); }
+
+int bvc_create(bvc_handle** out, const bvc_config* cfg) {
+    REQUIRE(out && cfg, BVC_ERR_INVALID, "bvc_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libbvc has no CPU path");
+        return BVC_ERR_DEVICE;
+    }
+    REQUIRE(cfg->device >= 0 && cfg->device < ndev, BVC_ERR_DEVICE, "bvc_create: bad device ordinal");
+    cudaDeviceProp prop;
+    BVC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        set_error(std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                  "; libbvc is built for sm_100a only");
+        return BVC_ERR_DEVICE;
+    }
+    REQUIRE(cfg->n_fft == 1024, BVC_ERR_INVALID, "n_fft must be 1024 in this build");
+    REQUIRE(cfg->hop > 0 && cfg->pad_left >= 0 && cfg->n_fft - cfg->pad_left - cfg->hop >= 0, BVC_ERR_INVALID,
+            "bad hop / pad_left");
+    REQUIRE(cfg->x_dim % 16 == 0 && cfg->h_dim % 32 == 0 && cfg->z_dim % 16 == 0, BVC_ERR_INVALID,
+            "x_dim, z_dim must be multiples of 16 and h_dim of 32");
+    REQUIRE(cfg->voc_num_stages == 4 && cfg->voc_num_kernels == 3 && cfg->voc_initial_channel == 128, BVC_ERR_INVALID,
+            "vocoder: this build covers the shipped 4-stage / 3-kernel / 128-channel configuration");
+    static const int up_ok[4] = {8, 8, 2, 2};
+    for (int i = 0; i < 4; ++i)
+        REQUIRE(cfg->voc_up_rates[i] == up_ok[i] && cfg->voc_up_kernels[i] == 2 * up_ok[i], BVC_ERR_INVALID,
+                "vocoder: upsample rates must be [8,8,2,2] with kernels [16,16,4,4]");
+    bvc_handle* h = new bvc_handle();
+    h->cfg = *cfg;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(cfg->device);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        delete h;
+        set_error("cudaStreamCreate failed");
+        return BVC_ERR_DEVICE;
+    }
+    *out = h;
+    return BVC_OK;
+}
+
+int bvc_destroy(bvc_handle* h) {
+    if (!h) return BVC_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->ws.base) cudaFree(h->ws.base);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaSetDevice(prev);
+    delete h;
+    return BVC_OK;
+}
+
+int bvc_set_precision(bvc_handle* h, int32_t mode) {
+    REQUIRE(h && (mode == 0 || mode == 1), BVC_ERR_INVALID, "precision mode must be 0 or 1");
+    h->precision = mode;
+    return BVC_OK;
+}
+
+int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
+    REQUIRE(h && tensors, BVC_ERR_INVALID, "bvc_load_bvrnn: null argument");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    TensorMap m;
+    int rc = collect(tensors, n, &m);
+    if (rc) return rc;
+    const int64_t X = h->cfg.x_dim, H = h->cfg.h_dim, Z = h->cfg.z_dim;
+    std::vector<std::pair<std::string, std::vector<int64_t>>> ex = {
+        {"mean_mel", {X}}, {"std_mel", {X}}, {"log_sigma", {1}},
+        {"rnn.weight_ih_l0", {3 * H, 2 * H}}, {"rnn.weight_hh_l0", {3 * H, H}},
+        {"rnn.bias_ih_l0", {3 * H}}, {"rnn.bias_hh_l0", {3 * H}}};
+    auto lin = [&](const std::string& name, int64_t o, int64_t i) {
+        ex.push_back({name + ".weight", {o, i}});
+        ex.push_back({name + ".bias", {o}});
+    };
+    lin("phi_x.0", H, X); lin("phi_x.2", H, H); lin("phi_x.4", H, H);
+    lin("phi_z.0", H, Z); lin("phi_z.2", H, H); lin("phi_z.4", H, H);
+    lin("enc.0", H, 2 * H); lin("enc.2", H, H); lin("enc.4", Z, H);
+    lin("prior.0", H, H); lin("prior.2", H, H); lin("prior.4", Z, H);
+    lin("dec.0", H, 2 * H); lin("dec.2", H, H); lin("dec.4", H, H); lin("dec.6", X, H);
+    rc = check_schema(m, ex);
+    if (rc) return rc;
+
+    BvrnnWeights& w = h->bw;
+    w.X = (int)X; w.H = (int)H; w.Z = (int)Z; w.var_bit = h->cfg.var_bit;
+    bool ok = true;
+    auto up = [&](const std::vector<float>& v) { float* p = dev_upload(h, v); ok = ok && p; return p; };
+    auto L = [&](const std::string& name, LinearWeights* lw, float** bias) {
+        const HostTensor& t = m[name + ".weight"];
+        ok = ok && make_linear(h, to_vec(t), (int)t.shape[0], (int)t.shape[1], lw);
+        *bias = up(to_vec(m[name + ".bias"]));
+    };
+    w.mean = up(to_vec(m["mean_mel"]));
+    w.std = up(to_vec(m["std_mel"]));
+    L("phi_x.0", &w.px0, &w.b_px0); L("phi_x.2", &w.px2, &w.b_px2); L("phi_x.4", &w.px4, &w.b_px4);
+    L("phi_z.0", &w.pz0, &w.b_pz0); L("phi_z.2", &w.pz2, &w.b_pz2); L("phi_z.4", &w.pz4, &w.b_pz4);
+    L("enc.2", &w.e2, &w.b_e2); L("enc.4", &w.e4, &w.b_e4);
+    L("dec.2", &w.d2, &w.b_d2); L("dec.4", &w.d4, &w.b_d4); L("dec.6", &w.d6, &w.b_d6);
+
+    const HostTensor &e0 = m["enc.0.weight"], &d0 = m["dec.0.weight"];
+    const HostTensor &wih = m["rnn.weight_ih_l0"], &whh = m["rnn.weight_hh_l0"];
+    const std::vector<float> zerosH((size_t)H, 0.f);
+    ok = ok && make_linear(h, slice(e0, 0, H, 0, H), (int)H, (int)H, &w.e0x);
+    {   // [enc.0[:, H:]; dec.0[:, H:]; W_hh]   (concat order of bvrnn.py:189,202: [phi ; h])
+        std::vector<float> c = slice(e0, 0, H, H, 2 * H);
+        append(c, slice(d0, 0, H, H, 2 * H));
+        append(c, to_vec(whh));
+        ok = ok && make_linear(h, c, (int)(5 * H), (int)H, &w.hcat_enc);
+        std::vector<float> b = to_vec(m["enc.0.bias"]);
+        append(b, zerosH);
+        append(b, to_vec(m["rnn.bias_hh_l0"]));
+        w.b_hcat_enc = up(b);
+    }
+    {
+        std::vector<float> c = slice(d0, 0, H, H, 2 * H);
+        append(c, to_vec(whh));
+        ok = ok && make_linear(h, c, (int)(4 * H), (int)H, &w.hcat_dec);
+        std::vector<float> b = zerosH;
+        append(b, to_vec(m["rnn.bias_hh_l0"]));
+        w.b_hcat_dec = up(b);
+    }
+    {   // [dec.0[:, :H]; W_ih[:, H:]]   (GRU input is [phi_x_gen ; phi_z], bvrnn.py:206)
+        std::vector<float> c = slice(d0, 0, H, 0, H);
+        append(c, slice(wih, 0, 3 * H, H, 2 * H));
+        ok = ok && make_linear(h, c, (int)(4 * H), (int)H, &w.zcat);
+        std::vector<float> b = to_vec(m["dec.0.bias"]);
+        append(b, to_vec(m["rnn.bias_ih_l0"]));
+        w.b_zcat = up(b);
+    }
+    ok = ok && make_linear(h, slice(wih, 0, 3 * H, 0, H), (int)(3 * H), (int)H, &w.ihx);
+    REQUIRE(ok, BVC_ERR_NOMEM, "device allocation failed while loading BVRNN weights");
+    h->have_bvrnn = true;
+    return BVC_OK;
+}
+
+int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
+    REQUIRE(h && tensors, BVC_ERR_INVALID, "bvc_load_vocoder: null argument");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    TensorMap m;
+    int rc = collect(tensors, n, &m);
+    if (rc) return rc;
+    const bvc_config& c = h->cfg;
+    const int64_t X = c.x_dim, C0 = c.voc_initial_channel;
+    std::vector<std::pair<std::string, std::vector<int64_t>>> ex;
+    auto wn = [&](const std::string& name, int64_t d0, int64_t d1, int64_t k, int64_t nb) {
+        ex.push_back({name + ".weight_g", {d0, 1, 1}});
+        ex.push_back({name + ".weight_v", {d0, d1, k}});
+        ex.push_back({name + ".bias", {nb}});
+    };
+    wn("conv_pre", C0, X, 7, C0);
+    int64_t ch = C0;
+    for (int i = 0; i < c.voc_num_stages; ++i) {
+        const int64_t cin = C0 >> i, cout = C0 >> (i + 1);
+        wn("ups." + std::to_string(i) + ".1", cin, cout, c.voc_up_kernels[i], cout);
+        ch = cout;
+        for (int j = 0; j < c.voc_num_kernels; ++j) {
+            const std::string rb = "resblocks." + std::to_string(i * c.voc_num_kernels + j);
+            for (int l = 0; l < 3; ++l) {
+                wn(rb + ".convs1." + std::to_string(l), ch, ch, c.voc_res_kernels[j], ch);
+                wn(rb + ".convs2." + std::to_string(l), ch, ch, c.voc_res_kernels[j], ch);
+            }
+            for (int a = 0; a < 6; ++a) {
+                ex.push_back({rb + ".activations." + std::to_string(a) + ".alpha", {ch}});
+                ex.push_back({rb + ".activations." + std::to_string(a) + ".beta", {ch}});
+            }
+        }
+    }
+    ex.push_back({"activation_post.alpha", {ch}});
+    ex.push_back({"activation_post.beta", {ch}});
+    wn("conv_post", 1, ch, 7, 1);
+    rc = check_schema(m, ex);
+    if (rc) return rc;
+
+    VocoderWeights& w = h->vw;
+    w.n_mels = (int)X; w.c0 = (int)C0; w.n_stages = c.voc_num_stages; w.n_kernels = c.voc_num_kernels;
+    for (int i = 0; i < 4; ++i) w.rates[i] = c.voc_up_rates[i];
+    for (int i = 0; i < 3; ++i) { w.dil[i] = c.voc_res_dilations[i]; w.rks[i] = c.voc_res_kernels[i]; }
+    bool ok = true;
+    auto up = [&](const std::vector<float>& v) { float* p = dev_upload(h, v); ok = ok && p; return p; };
+    auto folded = [&](const std::string& name) { return fold_weight_norm(m[name + ".weight_g"], m[name + ".weight_v"]); };
+    auto snake = [&](const std::string& name, int64_t C, SnakeParams* sp) {
+        const HostTensor &al = m[name + ".alpha"], &be = m[name + ".beta"];
+        std::vector<float> ea((size_t)C), ieb((size_t)C);
+        for (int64_t i = 0; i < C; ++i) {
+            ea[i] = expf(al.data[i]);
+            ieb[i] = 1.0f / (expf(be.data[i]) + 1e-9f);
+        }
+        sp->ea = up(ea);
+        sp->inv_eb = up(ieb);
+    };
+    {   // conv_pre [co, ci, 7] -> Linear over 7 contiguous channel-last frames: [co, j*X + ci]
+        const std::vector<float> f = folded("conv_pre");
+        std::vector<float> p((size_t)C0 * 7 * X);
+        for (int64_t co = 0; co < C0; ++co)
+            for (int64_t ci = 0; ci < X; ++ci)
+                for (int64_t j = 0; j < 7; ++j) p[(co * 7 + j) * X + ci] = f[(co * X + ci) * 7 + j];
+        ok = ok && make_linear(h, p, (int)C0, (int)(7 * X), &w.pre);
+        w.b_pre = up(to_vec(m["conv_pre.bias"]));
+    }
+    ch = C0;
+    for (int i = 0; i < w.n_stages; ++i) {
+        const int64_t cin = C0 >> i, cout = C0 >> (i + 1), k = c.voc_up_kernels[i];
+        const std::string un = "ups." + std::to_string(i) + ".1";
+        {   // ConvTranspose1d weight [ci, co, tap] -> [tap][ci][co]
+            const std::vector<float> f = folded(un);
+            std::vector<float> p(f.size());
+            for (int64_t ci = 0; ci < cin; ++ci)
+                for (int64_t co = 0; co < cout; ++co)
+                    for (int64_t t = 0; t < k; ++t) p[(t * cin + ci) * cout + co] = f[(ci * cout + co) * k + t];
+            w.w_up[i] = up(p);
+            w.b_up[i] = up(to_vec(m[un + ".bias"]));
+        }
+        ch = cout;
+        for (int j = 0; j < w.n_kernels; ++j) {
+            AmpBlockWeights& bw = w.blocks[i * w.n_kernels + j];
+            const std::string rb = "resblocks." + std::to_string(i * w.n_kernels + j);
+            const int64_t kk = c.voc_res_kernels[j];
+            bw.k = (int)kk;
+            auto pack = [&](const std::string& name) {   // [co, ci, tap] -> [ci][tap][co]
+                const std::vector<float> f = folded(name);
+                std::vector<float> p(f.size());
+                for (int64_t co = 0; co < ch; ++co)
+                    for (int64_t ci = 0; ci < ch; ++ci)
+                        for (int64_t t = 0; t < kk; ++t) p[(ci * kk + t) * ch + co] = f[(co * ch + ci) * kk + t];
+                return up(p);
+            };
+            for (int l = 0; l < 3; ++l) {
+                bw.w1[l] = pack(rb + ".convs1." + std::to_string(l));
+                bw.b1[l] = up(to_vec(m[rb + ".convs1." + std::to_string(l) + ".bias"]));
+                bw.w2[l] = pack(rb + ".convs2." + std::to_string(l));
+                bw.b2[l] = up(to_vec(m[rb + ".convs2." + std::to_string(l) + ".bias"]));
+            }
+            for (int a = 0; a < 6; ++a) snake(rb + ".activations." + std::to_string(a), ch, &bw.act[a]);
+        }
+    }
+    snake("activation_post", ch, &w.act_post);
+    w.w_post = up(folded("conv_post"));   // [1, ci, 7] is already [ci][tap]
+    w.b_post = up(to_vec(m["conv_post.bias"]));
+    REQUIRE(ok, BVC_ERR_NOMEM, "device allocation failed while loading vocoder weights");
+    h->have_voc = true;
+    return BVC_OK;
+}
+
+int bvc_set_frontend(bvc_handle* h, const float* window, const float* mel_basis) {
+    REQUIRE(h && window && mel_basis, BVC_ERR_INVALID, "bvc_set_frontend: null argument");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    const int N = h->cfg.n_fft, nb = N / 2 + 1, M = h->cfg.x_dim;
+    std::vector<float> win(window, window + N);
+    std::vector<float2> tw(N);
+    for (int q = 0; q < N; ++q) {
+        const double a = -2.0 * M_PI * q / N;
+        tw[q] = make_float2((float)cos(a), (float)sin(a));
+    }
+    std::vector<int> start(M, 0), count(M, 0);
+    int width = 1, used = 1;
+    for (int m = 0; m < M; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < nb; ++k)
+            if (mel_basis[(size_t)m * nb + k] != 0.f) { if (first < 0) first = k; last = k; }
+        if (first >= 0) {
+            start[m] = first;
+            count[m] = last - first + 1;
+            if (count[m] > width) width = count[m];
+            if (last + 1 > used) used = last + 1;
+        }
+    }
+    std::vector<float> taps((size_t)M * width, 0.f);
+    for (int m = 0; m < M; ++m)
+        for (int i = 0; i < count[m]; ++i) taps[(size_t)m * width + i] = mel_basis[(size_t)m * nb + start[m] + i];
+    FrontendTables& ft = h->ft;
+    ft.window = dev_upload(h, win);
+    ft.twiddle = dev_upload(h, tw);
+    ft.mel_start = dev_upload(h, start);
+    ft.mel_count = dev_upload(h, count);
+    ft.mel_taps = dev_upload(h, taps);
+    ft.mel_width = width;
+    ft.n_mels = M;
+    ft.n_bins_used = used;
+    REQUIRE(ft.window && ft.twiddle && ft.mel_start && ft.mel_count && ft.mel_taps, BVC_ERR_NOMEM,
+            "device allocation failed in bvc_set_frontend");
+    h->have_frontend = true;
+    return BVC_OK;
+}
+
+int bvc_logmel(bvc_handle* h, const float* x_dev, int32_t B, int32_t L, float scale, float* mel_dev, void* stream) {
+    REQUIRE(h && x_dev && mel_dev, BVC_ERR_INVALID, "bvc_logmel: null argument");
+    REQUIRE(h->have_frontend, BVC_ERR_STATE, "bvc_logmel: front-end tables not set");
+    const int need = h->cfg.n_fft - h->cfg.pad_left - h->cfg.hop;
+    REQUIRE(B > 0 && L > need && L > h->cfg.pad_left, BVC_ERR_INVALID,
+            "bvc_logmel: reflect padding needs L > " + std::to_string(need > h->cfg.pad_left ? need : h->cfg.pad_left));
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    return logmel_forward(h->ft, x_dev, B, L, h->cfg.hop, h->cfg.pad_left, scale, mel_dev, (cudaStream_t)stream);
+}
+
+int bvc_encode(bvc_handle* h, const float* mel_dev, const float* bits_dev, float bits_scalar, const float* h0_dev,
+               int32_t B, int32_t T, float* codes_dev, uint64_t* packed_dev, float* logits_dev, float* all_h_dev,
+               float* h_final_dev, void* stream) {
+    REQUIRE(h && mel_dev && codes_dev, BVC_ERR_INVALID, "bvc_encode: null argument");
+    REQUIRE(h->have_bvrnn, BVC_ERR_STATE, "bvc_encode: BVRNN weights not loaded");
+    REQUIRE(B > 0 && T >= 0, BVC_ERR_INVALID, "bvc_encode: bad B/T");
+    if (T == 0) return BVC_OK;
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    int rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T));
+    if (rc) return rc;
+    return bvrnn_encode(h->bw, h->ws, mel_dev, bits_dev, bits_scalar, h0_dev, B, T, codes_dev,
+                        (unsigned long long*)packed_dev, logits_dev, all_h_dev, h_final_dev, h->precision,
+                        (cudaStream_t)stream);
+}
+
+int bvc_decode_mel(bvc_handle* h, const float* codes_dev, const float* h0_dev, int32_t B, int32_t T, float* mel_dev,
+                   float* h_final_dev, void* stream) {
+    REQUIRE(h && codes_dev && mel_dev, BVC_ERR_INVALID, "bvc_decode_mel: null argument");
+    REQUIRE(h->have_bvrnn, BVC_ERR_STATE, "bvc_decode_mel: BVRNN weights not loaded");
+    REQUIRE(B > 0 && T >= 0, BVC_ERR_INVALID, "bvc_decode_mel: bad B/T");
+    if (T == 0) return BVC_OK;
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    int rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T));
+    if (rc) return rc;
+    return bvrnn_decode(h->bw, h->ws, codes_dev, h0_dev, B, T, mel_dev, h_final_dev, h->precision,
+                        (cudaStream_t)stream);
+}
+
+int64_t bvc_vocoder_out_len(const bvc_handle* h, int32_t T) {
+    if (!h) return -1;
+    int64_t n = T;
+    for (int i = 0; i < h->cfg.voc_num_stages; ++i) n = (n + 1) * h->cfg.voc_up_rates[i];
+    return n;
+}
+
+int bvc_vocode(bvc_handle* h, const float* mel_dev, int32_t B, int32_t T, int32_t length, float inv_scale_div,
+               float* wav_dev, void* stream) {
+    REQUIRE(h && mel_dev && wav_dev, BVC_ERR_INVALID, "bvc_vocode: null argument");
+    REQUIRE(h->have_voc, BVC_ERR_STATE, "bvc_vocode: vocoder weights not loaded");
+    REQUIRE(B > 0 && T > 0 && length >= 0, BVC_ERR_INVALID, "bvc_vocode: bad B/T/length");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    int rc = ensure_workspace(h, vocoder_workspace_floats(h->vw, B, T));
+    if (rc) return rc;
+    return vocoder_forward(h->vw, h->ws, h->vb, mel_dev, B, T, length, inv_scale_div, wav_dev, h->precision,
+                           (cudaStream_t)stream);
+}
+
+int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, float scale, float bits_scalar,
+                    float* codes_host) {
+    REQUIRE(h && x_host && codes_host, BVC_ERR_INVALID, "bvc_encode_host: null argument");
+    REQUIRE(h->have_bvrnn && h->have_frontend, BVC_ERR_STATE, "bvc_encode_host: weights / front-end not loaded");
+    const int need = h->cfg.n_fft - h->cfg.pad_left - h->cfg.hop;
+    REQUIRE(B > 0 && L > need && L > h->cfg.pad_left, BVC_ERR_INVALID, "bvc_encode_host: L too short for reflect padding");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    const int T = L / h->cfg.hop, X = h->cfg.x_dim, Z = h->cfg.z_dim;
+    const size_t nx = (size_t)B * L, nmel = (size_t)B * T * X, ncodes = (size_t)B * T * Z;
+    int rc = ensure_workspace(h, nx + nmel + ncodes + 256 + bvrnn_workspace_floats(h->bw, B, T));
+    if (rc) return rc;
+    float* x_dev = h->ws.take(nx);
+    float* mel = h->ws.take(nmel);
+    float* codes = h->ws.take(ncodes);
+    cudaStream_t s = h->stream;
+    BVC_CUDA(cudaMemcpyAsync(x_dev, x_host, nx * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = logmel_forward(h->ft, x_dev, B, L, h->cfg.hop, h->cfg.pad_left, scale, mel, s);
+    if (rc) return rc;
+    if (T > 0) {
+        rc = bvrnn_encode(h->bw, h->ws, mel, nullptr, bits_scalar, nullptr, B, T, codes, nullptr, nullptr, nullptr,
+                          nullptr, h->precision, s);
+        if (rc) return rc;
+        BVC_CUDA(cudaMemcpyAsync(codes_host, codes, ncodes * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    BVC_CUDA(cudaStreamSynchronize(s));
+    return BVC_OK;
+}
+
+int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T, int32_t length, float inv_scale_div,
+                    float* wav_host) {
+    REQUIRE(h && codes_host && wav_host, BVC_ERR_INVALID, "bvc_decode_host: null argument");
+    REQUIRE(h->have_bvrnn && h->have_voc, BVC_ERR_STATE, "bvc_decode_host: weights not loaded");
+    REQUIRE(B > 0 && T > 0 && length >= 0, BVC_ERR_INVALID, "bvc_decode_host: bad B/T/length");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    const int X = h->cfg.x_dim, Z = h->cfg.z_dim;
+    const int64_t n_full = bvc_vocoder_out_len(h, T);
+    const size_t n_out = (size_t)(length < n_full ? length : n_full);
+    const size_t ncodes = (size_t)B * T * Z, nmel = (size_t)B * T * X, nwav = (size_t)B * n_out;
+    int rc = ensure_workspace(h, ncodes + nmel + nwav + 256 + bvrnn_workspace_floats(h->bw, B, T) +
+                                     vocoder_workspace_floats(h->vw, B, T));
+    if (rc) return rc;
+    float* codes = h->ws.take(ncodes);
+    float* mel = h->ws.take(nmel);
+    float* wav = h->ws.take(nwav);
+    cudaStream_t s = h->stream;
+    BVC_CUDA(cudaMemcpyAsync(codes, codes_host, ncodes * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = bvrnn_decode(h->bw, h->ws, codes, nullptr, B, T, mel, nullptr, h->precision, s);
+    if (rc) return rc;
+    rc = vocoder_forward(h->vw, h->ws, h->vb, mel, B, T, length, inv_scale_div, wav, h->precision, s);
+    if (rc) return rc;
+    if (nwav) BVC_CUDA(cudaMemcpyAsync(wav_host, wav, nwav * sizeof(float), cudaMemcpyDeviceToHost, s));
+    BVC_CUDA(cudaStreamSynchronize(s));
+    return BVC_OK;
+}
+
+size_t bvc_workspace_bytes(const bvc_handle* h) { return h ? h->ws.bytes : 0; }
+int64_t bvc_kernel_launches(const bvc_handle* h) { return h ? h->launches : 0; }
+
+int bvc_debug_read(bvc_handle* h, const char* name, float* dst_host, size_t n_floats) {
+    REQUIRE(h && name && dst_host, BVC_ERR_INVALID, "bvc_debug_read: null argument");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    const VocoderBuffers& vb = h->vb;
+    const float* src = nullptr;
+    size_t avail = 0;
+    const std::string nm(name);
+    if (nm == "voc_pre") {
+        src = vb.pre;
+        avail = (size_t)vb.B * (vb.T + 6) * h->vw.c0;
+    } else if (nm.rfind("voc_stage", 0) == 0 && nm.size() == 12 && nm[10] == '_') {
+        const int i = nm[9] - '0', j = nm[11] - '0';
+        if (i >= 0 && i < 4 && j >= 0 && j < 3) {
+            src = vb.part[i][j];
+            avail = (size_t)vb.B * vb.C[i + 1] * vb.n[i + 1];
+        }
+    }
+    REQUIRE(src && vb.B > 0, BVC_ERR_INVALID, "bvc_debug_read: unknown buffer or no vocoder call yet: " + nm);
+    REQUIRE(n_floats <= avail, BVC_ERR_INVALID, "bvc_debug_read: buffer holds fewer floats than requested");
+    BVC_CUDA(cudaDeviceSynchronize());
+    BVC_CUDA(cudaMemcpy(dst_host, src, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    return BVC_OK;
+}
+
+}  // extern "C"

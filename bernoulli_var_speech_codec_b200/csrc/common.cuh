@@ -1,0 +1,164 @@
+// Shared declarations for libbvc (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "bvc.h"
+
+namespace bvc {
+
+void set_error(const std::string& msg);
+extern thread_local int64_t* g_launch_counter;   // points at the active handle's counter
+
+#define BVC_CUDA(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ::bvc::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+            return BVC_ERR_DEVICE;                                                       \
+        }                                                                                \
+    } while (0)
+
+#define BVC_CHECK_LAUNCH()                                                               \
+    do {                                                                                 \
+        if (::bvc::g_launch_counter) ++*::bvc::g_launch_counter;                         \
+        cudaError_t _e = cudaGetLastError();                                             \
+        if (_e != cudaSuccess) {                                                         \
+            ::bvc::set_error(std::string("kernel launch failed at ") + __FILE__ + ":" +  \
+                             std::to_string(__LINE__) + ": " + cudaGetErrorString(_e));  \
+            return BVC_ERR_DEVICE;                                                       \
+        }                                                                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Linear layer  C = epilogue(A . W^T)          (gemm.cu)
+// A [M, K] row stride lda, W [N, K] row stride K (nn.Linear layout), fp32.
+// ---------------------------------------------------------------------------
+struct LinearEpilogue {
+    const float* bias = nullptr;     // [N]
+    const float* addend = nullptr;   // [M, ldadd], added for columns n < n_add
+    int ldadd = 0;
+    int n_add = 0;
+    int n_act = 0;                   // ELU on columns n < n_act
+    float* out = nullptr;            // [M, ldo]
+    int ldo = 0;
+    // optional second output: (v - nmean[n]) / nstd[n]
+    const float* nmean = nullptr;
+    const float* nstd = nullptr;
+    float* out2 = nullptr;
+    int ldo2 = 0;
+};
+
+struct LinearWeights {
+    const float* w = nullptr;        // fp32 [N, K]
+    const uint32_t* w_hi = nullptr;  // split-bf16 copies packed for the tensor-core path (may be null)
+    const uint32_t* w_lo = nullptr;
+    int N = 0, K = 0;
+};
+
+int linear_forward(const float* A, int lda, int M, const LinearWeights& W, const LinearEpilogue& ep,
+                   int precision, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// log-mel front end (logmel.cu)
+// ---------------------------------------------------------------------------
+struct FrontendTables {
+    float* window = nullptr;      // [1024]
+    float2* twiddle = nullptr;    // [1024] exp(-2 pi i q / 1024)
+    int* mel_start = nullptr;     // [n_mels]
+    int* mel_count = nullptr;     // [n_mels]
+    float* mel_taps = nullptr;    // [n_mels, mel_width]
+    int mel_width = 0;
+    int n_mels = 0;
+    int n_bins_used = 0;          // highest non-zero FFT bin + 1
+};
+int logmel_forward(const FrontendTables& ft, const float* x, int B, int L, int hop, int pad_left, float scale,
+                   float* mel, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// BVRNN coder (bvrnn.cu)
+// ---------------------------------------------------------------------------
+struct BvrnnWeights {
+    int X = 0, H = 0, Z = 0, var_bit = 0;
+    float *mean = nullptr, *std = nullptr;
+    LinearWeights px0, px2, px4;      // phi_x
+    LinearWeights pz0, pz2, pz4;      // phi_z
+    LinearWeights e0x;                // enc.0[:, :H]      (hoisted over all frames, no bias)
+    LinearWeights e2, e4;
+    LinearWeights d2, d4, d6;
+    LinearWeights hcat_enc;           // [enc.0[:,H:]; dec.0[:,H:]; W_hh]   N = 5H   (input h)
+    LinearWeights hcat_dec;           // [dec.0[:,H:]; W_hh]                N = 4H   (input h)
+    LinearWeights zcat;               // [dec.0[:,:H]; W_ih[:,H:]]          N = 4H   (input phi_z)
+    LinearWeights ihx;                // W_ih[:, :H]                        N = 3H   (input phi_x_gen)
+    float *b_px0, *b_px2, *b_px4, *b_pz0, *b_pz2, *b_pz4, *b_e2, *b_e4, *b_d2, *b_d4, *b_d6;
+    float *b_hcat_enc, *b_hcat_dec, *b_zcat, *b_zcat_nod0;
+};
+
+struct Workspace {
+    float* base = nullptr;
+    size_t bytes = 0;
+    size_t used = 0;
+    float* take(size_t n_floats) {
+        size_t off = (used + 63) & ~size_t(63);
+        used = off + n_floats;
+        return base + off;
+    }
+};
+
+size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T);
+int bvrnn_encode(const BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
+                 const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
+                 float* all_h, float* h_final, int precision, cudaStream_t stream);
+int bvrnn_decode(const BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T,
+                 float* mel, float* h_final, int precision, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// causal BigVGAN-tiny vocoder (vocoder.cu)
+// ---------------------------------------------------------------------------
+struct SnakeParams {
+    float* ea = nullptr;      // exp(alpha)            [C]
+    float* inv_eb = nullptr;  // 1 / (exp(beta) + 1e-9) [C]
+};
+struct AmpBlockWeights {
+    int k = 0;
+    // per layer l in 0..2: conv1 (dilated) and conv2, weights repacked [ci][tap][co], fp32
+    float* w1[3];
+    float* b1[3];
+    float* w2[3];
+    float* b2[3];
+    SnakeParams act[6];
+};
+struct VocoderWeights {
+    int n_mels = 0, c0 = 0, n_stages = 0, n_kernels = 0;
+    int rates[4], dil[3], rks[3];
+    LinearWeights pre;        // conv_pre as a Linear over 7 contiguous mel frames: [c0, 7*n_mels], index j*n_mels+ci
+    float* b_pre = nullptr;
+    float* w_up[4];           // ConvTranspose weights repacked [tap][ci][co]
+    float* b_up[4];
+    AmpBlockWeights blocks[12];
+    SnakeParams act_post;
+    float* w_post = nullptr;  // [ci][tap]
+    float* b_post = nullptr;  // [1]
+};
+struct VocoderBuffers {       // views into the workspace, valid after the last vocoder_forward
+    float* mel_pad = nullptr; // [B, T+6, n_mels]
+    float* pre = nullptr;     // [B, T+6, c0] channel-last (rows t >= T of each utterance are scratch)
+    float* part[4][3];        // per stage, per resblock: [B, C, n]
+    int64_t n[5];             // n[0] = T, n[i+1] = length after stage i
+    int C[5];
+    int B = 0, T = 0;
+};
+size_t vocoder_workspace_floats(const VocoderWeights& w, int B, int T);
+int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, const float* mel, int B, int T,
+                    int length, float inv_scale_div, float* wav, int precision, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+}  // namespace bvc

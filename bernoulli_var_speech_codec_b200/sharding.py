@@ -1,0 +1,65 @@
+"""Utterance sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+Utterances are independent (reference bvrnn.py:186-206 works row-wise, the vocoder per item), so
+a batch is split into contiguous shards, each rank runs the whole encode->decode path on its
+shard with replicated weights, and the only collective is the final gather of codes / audio
+(NCCL over NVLink on GPUs; gloo in the CPU tests of the host logic).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, world_size: int, rank: int):
+    """Contiguous, balanced split: the first (n_items % world_size) ranks get one extra item."""
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def local_shard(x: torch.Tensor, group=None) -> torch.Tensor:
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(x.shape[0], ws, rk)
+    return x[lo:hi]
+
+
+def gather_shards(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All ranks receive the concatenation of every rank's shard (dim 0), ragged shards allowed."""
+    ws = dist.get_world_size(group)
+    if ws == 1:
+        return local
+    sizes = [shard_bounds(n_total, ws, r) for r in range(ws)]
+    max_n = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((ws * max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    parts = [out[r * max_n: r * max_n + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
+    return torch.cat(parts, 0)
+
+
+class ShardedCodec:
+    """Runs ``codec.encode`` / ``codec.decode`` on this rank's shard and gathers the results.
+
+    ``codec`` is any object with the reference API (``encode(x, bitrate)``, ``decode(codes, length)``).
+    """
+
+    def __init__(self, codec, group=None):
+        self.codec = codec
+        self.group = group
+
+    def encode(self, x_full: torch.Tensor, bitrate, gather: bool = True):
+        codes = self.codec.encode(local_shard(x_full, self.group), bitrate)
+        return gather_shards(codes, x_full.shape[0], self.group) if gather else codes
+
+    def decode(self, codes_full: torch.Tensor, length: int, gather: bool = True):
+        wav = self.codec.decode(local_shard(codes_full, self.group), length)
+        return gather_shards(wav, codes_full.shape[0], self.group) if gather else wav
+
+    def forward(self, x_full: torch.Tensor, bitrate, gather: bool = True):
+        xl = local_shard(x_full, self.group)
+        wav = self.codec.decode(self.codec.encode(xl, bitrate), x_full.shape[1])
+        return gather_shards(wav, x_full.shape[0], self.group) if gather else wav
+
+    __call__ = forward

@@ -1,0 +1,156 @@
+/*
+ * bvc.h -- C ABI of libbvc.so, the B200 (sm_100a) implementation of the batched
+ * BVRNN speech-codec encode -> decode hot path.
+ *
+ * The reference (BenjSta/bernoulli-var-speech-codec) has no FFI layer: its
+ * boundary is the Python nn.Module API (bvrnn_codec_model.py:19-76).  This
+ * header is the boundary a binding for that API talks to; each entry point
+ * names the reference function it replaces.  The Python facade
+ * (bernoulli_var_speech_codec_b200/codec.py) binds it with ctypes, see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative bvc_status otherwise;
+ *     bvc_last_error() returns a thread-local message for the last failure.
+ *     No exceptions cross the ABI.
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host"
+ *     pointers are ordinary (ideally page-locked) host memory.  The caller
+ *     owns every input/output buffer; the handle owns packed weights and
+ *     workspace.
+ *   - `stream` is a cudaStream_t passed as void*.  Device entry points only
+ *     enqueue work on it (no host synchronisation) unless stated otherwise.
+ *   - one handle per device; calls on one handle must be serialised by the
+ *     caller.
+ *   - there is no CPU path: bvc_create fails with BVC_ERR_DEVICE when the
+ *     device is not compute capability 10.x.
+ *   - layouts are row-major, innermost dimension last, float32 unless noted.
+ */
+#ifndef BVC_H_
+#define BVC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVC_ABI_VERSION 1
+
+typedef enum bvc_status {
+    BVC_OK = 0,
+    BVC_ERR_INVALID = -1,   /* bad argument / shape                                  */
+    BVC_ERR_SCHEMA = -2,    /* checkpoint tensor missing, unexpected or mis-shaped    */
+    BVC_ERR_DEVICE = -3,    /* no sm_100 device, or a CUDA runtime error              */
+    BVC_ERR_STATE = -4,     /* weights / front-end tables not loaded yet              */
+    BVC_ERR_NOMEM = -5
+} bvc_status;
+
+typedef struct bvc_handle bvc_handle;
+
+/* Model hyper-parameters: the keys the reference reads from its TOML config
+ * (configs/config_varBitRate.toml:21-29,35-37,39-56; bvrnn_codec_model.py:27-36). */
+typedef struct bvc_config {
+    int32_t device;            /* CUDA device ordinal                                  */
+    int32_t x_dim;             /* num_mels, 80                                         */
+    int32_t h_dim;             /* 1024                                                 */
+    int32_t z_dim;             /* 64                                                   */
+    int32_t var_bit;           /* 1: bits >= bits-per-frame are masked to 0.5          */
+    int32_t n_fft;             /* winsize, 1024 (must be 1024 in this build)           */
+    int32_t hop;               /* hopsize, 256                                         */
+    int32_t pad_left;          /* mel_pad_left, 256                                    */
+    int32_t voc_initial_channel;       /* 128                                          */
+    int32_t voc_num_stages;            /* 4                                            */
+    int32_t voc_up_rates[4];           /* 8,8,2,2                                      */
+    int32_t voc_up_kernels[4];         /* 16,16,4,4 (must equal 2*rate)                */
+    int32_t voc_num_kernels;           /* 3                                            */
+    int32_t voc_res_kernels[3];        /* 3,7,11                                       */
+    int32_t voc_res_dilations[3];      /* 1,3,5 (same for every resblock)              */
+} bvc_config;
+
+/* One named checkpoint tensor, float32, contiguous, in HOST memory. */
+typedef struct bvc_tensor {
+    const char* name;          /* state-dict key, e.g. "phi_x.0.weight"               */
+    const float* data;         /* host pointer                                         */
+    int32_t ndim;
+    int64_t shape[4];
+} bvc_tensor;
+
+int bvc_abi_version(void);
+const char* bvc_last_error(void);
+
+/* bvrnn_codec_model.py:20-36 (module construction). */
+int bvc_create(bvc_handle** out, const bvc_config* cfg);
+int bvc_destroy(bvc_handle* h);
+
+/* bvrnn_codec_model.py:38,41 -- strict load of the 'vrnn' state dict (39 tensors,
+ * schema SURVEY.md 3.1).  Unknown, missing or mis-shaped tensors fail with
+ * BVC_ERR_SCHEMA.  prior.* and log_sigma are accepted and unused. */
+int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n);
+
+/* bvrnn_codec_model.py:39,42 -- strict load of the 'generator' state dict
+ * (weight_g / weight_v / bias triplets, snake alpha / beta).  weight-norm is
+ * folded here once (third_party/BigVGAN/models.py:47-62,140,164,200). */
+int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n);
+
+/* Front-end constant tables (meldataset.py:67-70): analysis window [n_fft] and
+ * the mel filterbank [n_mels, n_fft/2+1] (dense, host memory). */
+int bvc_set_frontend(bvc_handle* h, const float* window, const float* mel_basis);
+
+/* third_party/BigVGAN/meldataset.py:60-95 (mel_spectrogram, incl. the x*SCALING
+ * of bvrnn_codec_model.py:49 through `scale`).
+ * x_dev [B, L] -> mel_dev [B, T, x_dim] with T = L / hop.  Requires L > n_fft - pad_left - hop. */
+int bvc_logmel(bvc_handle* h, const float* x_dev, int32_t B, int32_t L, float scale,
+               float* mel_dev, void* stream);
+
+/* bvrnn.py:163-209 (BVRNN.encode).
+ * mel_dev [B,T,x_dim]; bits_dev [B,T] bits per frame (float, like the reference's
+ * varBitrate) or NULL -> bits_scalar for every frame; h0_dev [B,h_dim] or NULL -> zeros.
+ * Outputs (each nullable except codes_dev):
+ *   codes_dev  [B,T,z_dim]  {0,1} active bits, 0.5 masked bits (bvrnn.py:191-196)
+ *   packed_dev [B,T] uint64 bit i of word = code i (masked bits 0)
+ *   logits_dev [B,T,z_dim]  pre-sigmoid encoder output (parity tap)
+ *   all_h_dev  [B,T,h_dim]  state entering frame t (bvrnn.py:205)
+ *   h_final_dev[B,h_dim]    state after the last frame */
+int bvc_encode(bvc_handle* h, const float* mel_dev, const float* bits_dev, float bits_scalar,
+               const float* h0_dev, int32_t B, int32_t T,
+               float* codes_dev, uint64_t* packed_dev, float* logits_dev,
+               float* all_h_dev, float* h_final_dev, void* stream);
+
+/* bvrnn.py:211-229 (BVRNN.decode).  codes_dev [B,T,z_dim] arbitrary floats. */
+int bvc_decode_mel(bvc_handle* h, const float* codes_dev, const float* h0_dev,
+                   int32_t B, int32_t T, float* mel_dev, float* h_final_dev, void* stream);
+
+/* third_party/BigVGAN/models.py:207-238 (BigVGAN.forward) followed by the
+ * division by SCALING of bvrnn_codec_model.py:71 (`inv_scale_div`: the output is
+ * tanh(.) / inv_scale_div; pass 1.0f for the bare vocoder).
+ * mel_dev [B,T,x_dim] (channel-last) -> wav_dev [B, n], n = min(length, 256*T+294). */
+int bvc_vocode(bvc_handle* h, const float* mel_dev, int32_t B, int32_t T, int32_t length,
+               float inv_scale_div, float* wav_dev, void* stream);
+int64_t bvc_vocoder_out_len(const bvc_handle* h, int32_t T);
+
+/* bvrnn_codec_model.py:44-62 / :64-71 with HOST buffers: host->device copy of the
+ * input, the whole stage chain, device->host copy of the result, and a stream
+ * synchronise before returning.  x_host [B,L] -> codes_host [B, L/hop, z_dim];
+ * codes_host [B,T,z_dim] -> wav_host [B, length]. */
+int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, float scale,
+                    float bits_scalar, float* codes_host);
+int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T, int32_t length,
+                    float inv_scale_div, float* wav_host);
+
+/* Bytes of device workspace the handle holds for a (B, T) job (grown on demand). */
+size_t bvc_workspace_bytes(const bvc_handle* h);
+/* Kernels launched by this library since the handle was created (bench evidence). */
+int64_t bvc_kernel_launches(const bvc_handle* h);
+/* Arithmetic mode of the GEMM/conv inner products: 0 = fp32 FFMA, 1 = split-bf16 tensor core. */
+int bvc_set_precision(bvc_handle* h, int32_t mode);
+
+/* Debug/parity taps: copy an internal device buffer of the LAST call to host.
+ * Names: "voc_pre" [B,T+6,128] channel-last, "voc_stage{0..3}_{0..2}" [B,C,n] partial sums.
+ * Synchronises the device. */
+int bvc_debug_read(bvc_handle* h, const char* name, float* dst_host, size_t n_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BVC_H_ */

@@ -1,0 +1,59 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA sm_100 device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def ckpts():
+    """Synthetic checkpoints with the reference's state-dict schema (seed/sharpen of the golden fixtures)."""
+    from bernoulli_var_speech_codec_b200.synth import write_synthetic_checkpoints
+    d = os.environ.get("BVC_CKPT_DIR", "/tmp/bvc_ckpts")
+    return write_synthetic_checkpoints(d, seed=1, sharpen=30.0)
+
+
+@pytest.fixture(scope="session")
+def cfg_var():
+    return os.path.join(ROOT, "configs", "config_varBitRate.toml")
+
+
+@pytest.fixture(scope="session")
+def cfg_fix():
+    return os.path.join(ROOT, "configs", "config_64bit.toml")
+
+
+@pytest.fixture(scope="session")
+def oracle_var(ckpts, cfg_var):
+    from oracle.codec_oracle import OracleCodec
+    return OracleCodec(cfg_var, *ckpts)
+
+
+@pytest.fixture(scope="session")
+def oracle_fix(ckpts, cfg_fix):
+    from oracle.codec_oracle import OracleCodec
+    return OracleCodec(cfg_fix, *ckpts)
+
+
+@pytest.fixture(scope="session")
+def model_var(ckpts, cfg_var):
+    from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
+    return BVRNNCodecModel(cfg_var, *ckpts).eval()
+
+
+@pytest.fixture(scope="session")
+def model_fix(ckpts, cfg_fix):
+    from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
+    return BVRNNCodecModel(cfg_fix, *ckpts).eval()
+
+
+def golden(name):
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", name))

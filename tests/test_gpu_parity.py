@@ -1,0 +1,190 @@
+"""GPU parity tests: the CUDA path (through the facade -> C ABI) against the CPU oracle and the
+golden vectors made by the unmodified reference.  Tolerances are stated per check.
+
+  codes   : bit-exact except bits within EPS_PROB=1e-4 of the decision threshold (counted, re-synced)
+  log-mel : max-abs <= 2e-4 (fp32 FFT / mel accumulation order)
+  dec mel : max-abs <= 5e-4 in fp32 mode, <= 5e-3 in split-bf16 mode
+  wave    : SNR >= 60 dB in fp32 mode, >= 40 dB in split-bf16 mode (output range +-3.16)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from parity import compare_codes, snr_db
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL = 2e-4
+
+
+def _noise(B, L, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (0.1 * torch.randn(B, L, generator=g)).clamp(-1, 1)
+
+
+def _check_case(model, oracle, x, bitrate, dec_tol=5e-4, snr_min=60.0):
+    dev = model.device
+    taps = {}
+    o_codes = oracle.encode(x, bitrate, taps)
+    xd = x.to(dev)
+    r = model.encode_with_taps(xd, bitrate)
+    assert (r["mel"].cpu() - taps["mel"]).abs().max() <= MEL_TOL
+    rep = compare_codes(model._engine, r["mel"], model.bits_per_frame(bitrate), o_codes, taps["logits"], taps["all_h"])
+    assert rep["hard_mismatches"] == 0 and rep["mask_errors"] == 0, rep
+    assert rep["eps_bits"] <= max(2, rep["total_bits"] // 2000), rep
+    o_taps = {}
+    o_wav = oracle.decode(o_codes, x.shape[1], o_taps)
+    dmel, _ = model._engine.decode_mel(o_codes.to(dev), None)
+    assert (dmel.cpu() - o_taps["dec_mel"]).abs().max() <= dec_tol
+    wav = model.decode(o_codes.to(dev), x.shape[1]).cpu()
+    assert wav.shape == o_wav.shape
+    assert snr_db(o_wav.numpy(), wav.numpy()) >= snr_min
+    return rep
+
+
+@pytest.mark.parametrize("name,which", [("synth_var_small.npz", "var"), ("synth_fix_small.npz", "fix")])
+def test_golden_small(name, which, model_var, model_fix, oracle_var, oracle_fix):
+    g = golden(name)
+    model, oracle = (model_var, oracle_var) if which == "var" else (model_fix, oracle_fix)
+    x = torch.from_numpy(g["x"])
+    _check_case(model, oracle, x, float(g["bitrate"]))
+    # and directly against the reference's own outputs
+    codes = model.encode(x.to(model.device), float(g["bitrate"])).cpu().numpy()
+    assert ((codes == 0.5) == (g["codes"] == 0.5)).all()
+    wav = model.decode(torch.from_numpy(g["codes"]).to(model.device), x.shape[1]).cpu().numpy()
+    assert snr_db(g["wav"], wav) >= 60.0
+
+
+def test_golden_config1_stim01(model_var, oracle_var):
+    """BASELINE config #1: MUSHRA stim_01 ref.wav at 3000 bps, batch 1."""
+    g = golden("stim01_var.npz")
+    x = torch.from_numpy(g["x"])
+    _check_case(model_var, oracle_var, x, 3000)
+    y = model_var(x.to(model_var.device), 3000)
+    assert y.shape == x.shape
+
+
+@pytest.mark.parametrize("tag,nbits", [("0", 0), ("1", 1), ("64", 64), ("gt64", 64)])
+def test_bit_budget_edges(tag, nbits, model_var, oracle_var):
+    g = golden(f"synth_var_bits_{tag}.npz")
+    x = torch.from_numpy(g["x"])
+    codes = model_var.encode(x.to(model_var.device), float(g["bitrate"])).cpu().numpy()
+    assert (codes[:, :, nbits:] == 0.5).all() and np.isin(codes[:, :, :nbits], (0.0, 1.0)).all()
+    _check_case(model_var, oracle_var, x, float(g["bitrate"]))
+
+
+def test_fixed_rate_ignores_bitrate(model_fix):
+    x = _noise(2, 4000, 3).to(model_fix.device)
+    a, b = model_fix.encode(x, 100), model_fix.encode(x, 5000)
+    assert torch.equal(a, b) and np.isin(a.cpu().numpy(), (0.0, 1.0)).all()
+
+
+def test_ragged_lengths_and_batch(model_var, oracle_var):
+    for L in (513, 1000, 256 * 9, 256 * 9 + 255):
+        x = _noise(3, L, L)
+        _check_case(model_var, oracle_var, x, 3000)
+        y = model_var(x.to(model_var.device), 3000)
+        assert y.shape == (3, L)
+
+
+def test_short_input_rejected(model_var):
+    with pytest.raises(RuntimeError):
+        model_var.encode(torch.zeros(1, 512, device=model_var.device), 3000)
+
+
+def test_batch_invariance_and_packed(model_var):
+    x = _noise(5, 6000, 7).to(model_var.device)
+    r = model_var.encode_with_taps(x, 3000)
+    r1 = model_var.encode_with_taps(x[2:3].contiguous(), 3000)
+    assert torch.equal(r["codes"][2:3], r1["codes"])
+    codes = r["codes"].cpu().numpy()
+    packed = r["packed"].cpu().numpy().astype(np.uint64)
+    bits = ((packed[..., None] >> np.arange(64, dtype=np.uint64)) & np.uint64(1)).astype(np.float32)
+    assert np.array_equal(bits == 1.0, codes == 1.0)
+
+
+def test_operator_level_api(model_var, oracle_var):
+    """BVRNN.encode/decode with per-frame bit budgets and carried state; BigVGAN.forward; mel_spectrogram."""
+    from bernoulli_var_speech_codec_b200 import mel_spectrogram, SCALING
+    from oracle.codec_oracle import bvrnn_encode
+    dev = model_var.device
+    x = _noise(2, 5000, 21)
+    mel_o = oracle_var.logmel(x)
+    mel = mel_spectrogram(x.to(dev) * SCALING, 1024, 80, 22050, 256, 1024, 0, 8000, 256)
+    assert mel.shape == (2, 80, mel_o.shape[1])
+    assert (mel.permute(0, 2, 1).cpu() - mel_o).abs().max() <= MEL_TOL
+    T = mel_o.shape[1]
+    bits = torch.randint(0, 70, (2, T)).float()
+    h0 = 0.1 * torch.randn(1, 2, 1024)
+    z_o, all_h_o, _ = bvrnn_encode(oracle_var.sd, mel_o, bits, h0[0], True)
+    z, all_h = model_var.bvrnn.encode(mel_o.to(dev), bits.to(dev), h0.to(dev))
+    assert z.shape == z_o.shape and all_h.shape == all_h_o.shape
+    assert ((z.cpu() == 0.5) == (z_o == 0.5)).all()
+    assert (z.cpu() != z_o).float().mean() < 1e-3
+    assert (all_h[:, 0].cpu() - h0[0]).abs().max() == 0
+    # decode in two chunks with carried h equals one pass (bit-identical)
+    m_full, h_full = model_var.bvrnn.decode(z_o.to(dev), torch.zeros(1, 2, 1024, device=dev))
+    m_a, h_a = model_var.bvrnn.decode(z_o[:, :7].to(dev), torch.zeros(1, 2, 1024, device=dev))
+    m_b, h_b = model_var.bvrnn.decode(z_o[:, 7:].contiguous().to(dev), h_a)
+    assert h_full.shape == (1, 2, 1024)
+    assert torch.equal(torch.cat([m_a, m_b], 1), m_full) and torch.equal(h_b, h_full)
+    # bare vocoder: (B,80,T) -> (B,1,length), no /SCALING
+    m_o, _ = oracle_var.decode_mel(z_o)
+    w_o = oracle_var.vocoder(m_o.permute(0, 2, 1), 5000)
+    w = model_var.vocoder(m_o.permute(0, 2, 1).to(dev), 5000)
+    assert w.shape == w_o.shape and snr_db(w_o.numpy(), w.cpu().numpy()) >= 60.0
+    assert model_var.vocoder(m_o.permute(0, 2, 1).to(dev), 10 ** 6).shape[-1] == 256 * T + 294
+
+
+def test_host_buffer_api_matches_device_api(model_var):
+    x = _noise(2, 7000, 9)
+    c_dev = model_var.encode(x.to(model_var.device), 3000)
+    c_host = model_var.encode(x, 3000)
+    assert c_host.device.type == "cpu" and torch.equal(c_host, c_dev.cpu())
+    w_dev = model_var.decode(c_dev, 7000)
+    w_host = model_var.decode(c_host, 7000)
+    assert w_host.device.type == "cpu" and torch.equal(w_host, w_dev.cpu())
+
+
+def test_strict_checkpoint_schema(ckpts, cfg_var, tmp_path):
+    from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
+    ck = torch.load(ckpts[0], map_location="cpu", weights_only=True)
+    bad = dict(ck["vrnn"])
+    bad.pop("enc.2.bias")
+    p = tmp_path / "bad"
+    torch.save({"vrnn": bad}, p)
+    with pytest.raises(RuntimeError, match="missing key"):
+        BVRNNCodecModel(cfg_var, str(p), ckpts[1])
+    bad = dict(ck["vrnn"])
+    bad["enc.4.weight"] = bad["enc.4.weight"][:32]
+    torch.save({"vrnn": bad}, p)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        BVRNNCodecModel(cfg_var, str(p), ckpts[1])
+
+
+def test_split_bf16_tensor_core_mode(ckpts, cfg_var, oracle_var):
+    """precision mode 1 (split-bf16 mma): same code protocol, looser float tolerances."""
+    from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
+    m = BVRNNCodecModel(cfg_var, *ckpts).eval()
+    m._engine.set_precision(1)
+    x = _noise(4, 8000, 33)
+    _check_case(m, oracle_var, x, 3000, dec_tol=5e-3, snr_min=40.0)
+
+
+def test_larger_batch_properties(model_var, oracle_var):
+    """B=16 x 2 s: oracle parity on a subset plus size-independent properties on the whole batch."""
+    B, L = 16, 44100
+    x = _noise(B, L, 1234)
+    xd = x.to(model_var.device)
+    codes = model_var.encode(xd, 3000)
+    c = codes.cpu().numpy()
+    assert c.shape == (B, L // 256, 64)
+    assert (c[:, :, 35:] == 0.5).all() and np.isin(c[:, :, :35], (0.0, 1.0)).all()
+    wav = model_var.decode(codes, L)
+    assert wav.shape == (B, L) and torch.isfinite(wav).all() and wav.abs().max() <= 1.0 / (10 ** (-10 / 20)) + 1e-4
+    assert torch.equal(model_var(xd, 3000), wav)                # forward == decode(encode)
+    # permutation equivariance over utterances (rows are independent)
+    perm = torch.randperm(B)
+    assert torch.equal(model_var.encode(xd[perm].contiguous(), 3000), codes[perm])
+    _check_case(model_var, oracle_var, x[:2], 3000)
