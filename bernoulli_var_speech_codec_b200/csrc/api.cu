@@ -31,6 +31,8 @@ struct bvc_handle {
     int precision = 0;
     std::vector<void*> allocs;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ws_event = nullptr;   // end of the last job that used the workspace (any stream)
+    bool ws_event_valid = false;
 };
 
 namespace {
@@ -177,6 +179,34 @@ std::vector<float> fold_weight_norm(const HostTensor& g, const HostTensor& v) {
     return w;
 }
 
+// Split-bf16 weights in mma.sync.m16n8k16 B-fragment order.  B[kk][co] with kk = tap * CIN + ci, zero padded
+// to a multiple of 16 rows; entry ((kc * NT + nt) * 32 + lane) holds (b0, b1) of that lane.
+template <typename Get>
+void pack_fragments(int ntaps, int CIN, int COUT, Get get, std::vector<uint2>* hi, std::vector<uint2>* lo) {
+    const int KT = ntaps * CIN, KC = (KT + 15) / 16, NT = COUT / 8;
+    hi->assign((size_t)KC * NT * 32, make_uint2(0, 0));
+    lo->assign((size_t)KC * NT * 32, make_uint2(0, 0));
+    for (int kc = 0; kc < KC; ++kc)
+        for (int nt = 0; nt < NT; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, q = lane & 3, n = nt * 8 + g;
+                uint32_t h2[2], l2[2];
+                for (int reg = 0; reg < 2; ++reg) {
+                    uint16_t hh[2], ll[2];
+                    for (int e = 0; e < 2; ++e) {
+                        const int kk = 16 * kc + 2 * q + 8 * reg + e;
+                        const float v = kk < KT ? get(kk / CIN, kk % CIN, n) : 0.f;
+                        hh[e] = f2bf(v);
+                        ll[e] = f2bf(v - bf2f(hh[e]));
+                    }
+                    h2[reg] = (uint32_t)hh[0] | ((uint32_t)hh[1] << 16);
+                    l2[reg] = (uint32_t)ll[0] | ((uint32_t)ll[1] << 16);
+                }
+                (*hi)[((size_t)kc * NT + nt) * 32 + lane] = make_uint2(h2[0], h2[1]);
+                (*lo)[((size_t)kc * NT + nt) * 32 + lane] = make_uint2(l2[0], l2[1]);
+            }
+}
+
 int ensure_workspace(bvc_handle* h, size_t floats) {
     const size_t bytes = floats * sizeof(float) + 4096;
     if (h->ws.bytes < bytes) {
@@ -196,6 +226,18 @@ int ensure_workspace(bvc_handle* h, size_t floats) {
         h->ws.bytes = bytes;
     }
     h->ws.used = 0;
+    return BVC_OK;
+}
+
+// The workspace is shared by every entry point.  Work is stream-ordered, so a job on stream s must
+// not start before the previous job (possibly on another stream) has finished with the workspace.
+int ws_acquire(bvc_handle* h, cudaStream_t s) {
+    if (h->ws_event_valid) BVC_CUDA(cudaStreamWaitEvent(s, h->ws_event, 0));
+    return BVC_OK;
+}
+int ws_release(bvc_handle* h, cudaStream_t s) {
+    BVC_CUDA(cudaEventRecord(h->ws_event, s));
+    h->ws_event_valid = true;
     return BVC_OK;
 }
 
@@ -248,6 +290,7 @@ int bvc_create(bvc_handle** out, const bvc_config* cfg) {
     cudaGetDevice(&prev);
     cudaSetDevice(cfg->device);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ws_event, cudaEventDisableTiming);
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
         delete h;
@@ -267,6 +310,7 @@ int bvc_destroy(bvc_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->ws_event) cudaEventDestroy(h->ws_event);
     cudaSetDevice(prev);
     delete h;
     return BVC_OK;
@@ -431,6 +475,20 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
                     for (int64_t t = 0; t < k; ++t) p[(t * cin + ci) * cout + co] = f[(ci * cout + co) * k + t];
             w.w_up[i] = up(p);
             w.b_up[i] = up(to_vec(m[un + ".bias"]));
+            // tensor-core copy: output phase r is a 2-tap conv over (x[j-1], x[j]) with taps (W[.,.,r+U], W[.,.,r])
+            const int64_t U = c.voc_up_rates[i];
+            std::vector<uint2> allh, alll;
+            for (int64_t r = 0; r < U; ++r) {
+                std::vector<uint2> fh, fl;
+                pack_fragments(2, (int)cin, (int)cout,
+                               [&](int tap, int ci, int co) { return f[((size_t)ci * cout + co) * k + (tap == 0 ? r + U : r)]; },
+                               &fh, &fl);
+                allh.insert(allh.end(), fh.begin(), fh.end());
+                alll.insert(alll.end(), fl.begin(), fl.end());
+            }
+            w.upf_h[i] = dev_upload(h, allh);
+            w.upf_l[i] = dev_upload(h, alll);
+            ok = ok && w.upf_h[i] && w.upf_l[i];
         }
         ch = cout;
         for (int j = 0; j < w.n_kernels; ++j) {
@@ -438,18 +496,24 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
             const std::string rb = "resblocks." + std::to_string(i * w.n_kernels + j);
             const int64_t kk = c.voc_res_kernels[j];
             bw.k = (int)kk;
-            auto pack = [&](const std::string& name) {   // [co, ci, tap] -> [ci][tap][co]
+            auto pack = [&](const std::string& name, uint2** fh_out, uint2** fl_out) {   // [co, ci, tap] -> [ci][tap][co]
                 const std::vector<float> f = folded(name);
                 std::vector<float> p(f.size());
                 for (int64_t co = 0; co < ch; ++co)
                     for (int64_t ci = 0; ci < ch; ++ci)
                         for (int64_t t = 0; t < kk; ++t) p[(ci * kk + t) * ch + co] = f[(co * ch + ci) * kk + t];
+                std::vector<uint2> fh, fl;
+                pack_fragments((int)kk, (int)ch, (int)ch,
+                               [&](int tap, int ci, int co) { return f[((size_t)co * ch + ci) * kk + tap]; }, &fh, &fl);
+                *fh_out = dev_upload(h, fh);
+                *fl_out = dev_upload(h, fl);
+                ok = ok && *fh_out && *fl_out;
                 return up(p);
             };
             for (int l = 0; l < 3; ++l) {
-                bw.w1[l] = pack(rb + ".convs1." + std::to_string(l));
+                bw.w1[l] = pack(rb + ".convs1." + std::to_string(l), &bw.f1h[l], &bw.f1l[l]);
                 bw.b1[l] = up(to_vec(m[rb + ".convs1." + std::to_string(l) + ".bias"]));
-                bw.w2[l] = pack(rb + ".convs2." + std::to_string(l));
+                bw.w2[l] = pack(rb + ".convs2." + std::to_string(l), &bw.f2h[l], &bw.f2l[l]);
                 bw.b2[l] = up(to_vec(m[rb + ".convs2." + std::to_string(l) + ".bias"]));
             }
             for (int a = 0; a < 6; ++a) snake(rb + ".activations." + std::to_string(a), ch, &bw.act[a]);
@@ -527,9 +591,12 @@ int bvc_encode(bvc_handle* h, const float* mel_dev, const float* bits_dev, float
     if (!g.ok) return BVC_ERR_DEVICE;
     int rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T));
     if (rc) return rc;
-    return bvrnn_encode(h->bw, h->ws, mel_dev, bits_dev, bits_scalar, h0_dev, B, T, codes_dev,
-                        (unsigned long long*)packed_dev, logits_dev, all_h_dev, h_final_dev, h->precision,
-                        (cudaStream_t)stream);
+    if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
+    rc = bvrnn_encode(h->bw, h->ws, mel_dev, bits_dev, bits_scalar, h0_dev, B, T, codes_dev,
+                      (unsigned long long*)packed_dev, logits_dev, all_h_dev, h_final_dev, h->precision,
+                      (cudaStream_t)stream);
+    if (rc) return rc;
+    return ws_release(h, (cudaStream_t)stream);
 }
 
 int bvc_decode_mel(bvc_handle* h, const float* codes_dev, const float* h0_dev, int32_t B, int32_t T, float* mel_dev,
@@ -542,8 +609,11 @@ int bvc_decode_mel(bvc_handle* h, const float* codes_dev, const float* h0_dev, i
     if (!g.ok) return BVC_ERR_DEVICE;
     int rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T));
     if (rc) return rc;
-    return bvrnn_decode(h->bw, h->ws, codes_dev, h0_dev, B, T, mel_dev, h_final_dev, h->precision,
-                        (cudaStream_t)stream);
+    if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
+    rc = bvrnn_decode(h->bw, h->ws, codes_dev, h0_dev, B, T, mel_dev, h_final_dev, h->precision,
+                      (cudaStream_t)stream);
+    if (rc) return rc;
+    return ws_release(h, (cudaStream_t)stream);
 }
 
 int64_t bvc_vocoder_out_len(const bvc_handle* h, int32_t T) {
@@ -562,8 +632,11 @@ int bvc_vocode(bvc_handle* h, const float* mel_dev, int32_t B, int32_t T, int32_
     if (!g.ok) return BVC_ERR_DEVICE;
     int rc = ensure_workspace(h, vocoder_workspace_floats(h->vw, B, T));
     if (rc) return rc;
-    return vocoder_forward(h->vw, h->ws, h->vb, mel_dev, B, T, length, inv_scale_div, wav_dev, h->precision,
-                           (cudaStream_t)stream);
+    if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
+    rc = vocoder_forward(h->vw, h->ws, h->vb, mel_dev, B, T, length, inv_scale_div, wav_dev, h->precision,
+                         (cudaStream_t)stream);
+    if (rc) return rc;
+    return ws_release(h, (cudaStream_t)stream);
 }
 
 int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, float scale, float bits_scalar,
@@ -582,6 +655,7 @@ int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, fl
     float* mel = h->ws.take(nmel);
     float* codes = h->ws.take(ncodes);
     cudaStream_t s = h->stream;
+    if ((rc = ws_acquire(h, s))) return rc;
     BVC_CUDA(cudaMemcpyAsync(x_dev, x_host, nx * sizeof(float), cudaMemcpyHostToDevice, s));
     rc = logmel_forward(h->ft, x_dev, B, L, h->cfg.hop, h->cfg.pad_left, scale, mel, s);
     if (rc) return rc;
@@ -591,6 +665,7 @@ int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, fl
         if (rc) return rc;
         BVC_CUDA(cudaMemcpyAsync(codes_host, codes, ncodes * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
+    if ((rc = ws_release(h, s))) return rc;
     BVC_CUDA(cudaStreamSynchronize(s));
     return BVC_OK;
 }
@@ -613,12 +688,14 @@ int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T
     float* mel = h->ws.take(nmel);
     float* wav = h->ws.take(nwav);
     cudaStream_t s = h->stream;
+    if ((rc = ws_acquire(h, s))) return rc;
     BVC_CUDA(cudaMemcpyAsync(codes, codes_host, ncodes * sizeof(float), cudaMemcpyHostToDevice, s));
     rc = bvrnn_decode(h->bw, h->ws, codes, nullptr, B, T, mel, nullptr, h->precision, s);
     if (rc) return rc;
     rc = vocoder_forward(h->vw, h->ws, h->vb, mel, B, T, length, inv_scale_div, wav, h->precision, s);
     if (rc) return rc;
     if (nwav) BVC_CUDA(cudaMemcpyAsync(wav_host, wav, nwav * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if ((rc = ws_release(h, s))) return rc;
     BVC_CUDA(cudaStreamSynchronize(s));
     return BVC_OK;
 }

@@ -124,11 +124,14 @@ struct SnakeParams {
 };
 struct AmpBlockWeights {
     int k = 0;
-    // per layer l in 0..2: conv1 (dilated) and conv2, weights repacked [ci][tap][co], fp32
-    float* w1[3];
+    // per layer l in 0..2: conv1 (dilated) and conv2
+    float* w1[3];   // fp32 [ci][tap][co]                       (FFMA path)
     float* b1[3];
     float* w2[3];
     float* b2[3];
+    // split-bf16 copies in mma.m16n8k16 B-fragment order: [k16 chunk][n8 tile][lane] -> uint2 (b0, b1),
+    // GEMM-K index = tap * C + ci                              (tensor-core path)
+    uint2 *f1h[3], *f1l[3], *f2h[3], *f2l[3];
     SnakeParams act[6];
 };
 struct VocoderWeights {
@@ -138,6 +141,7 @@ struct VocoderWeights {
     float* b_pre = nullptr;
     float* w_up[4];           // ConvTranspose weights repacked [tap][ci][co]
     float* b_up[4];
+    uint2 *upf_h[4], *upf_l[4];   // per output phase r: 2-tap fragment-packed weights (taps r+U, r), phases concatenated
     AmpBlockWeights blocks[12];
     SnakeParams act_post;
     float* w_post = nullptr;  // [ci][tap]
@@ -146,7 +150,7 @@ struct VocoderWeights {
 struct VocoderBuffers {       // views into the workspace, valid after the last vocoder_forward
     float* mel_pad = nullptr; // [B, T+6, n_mels]
     float* pre = nullptr;     // [B, T+6, c0] channel-last (rows t >= T of each utterance are scratch)
-    float* part[4][3];        // per stage, per resblock: [B, C, n]
+    float* part[4][3];        // per stage, per resblock: [B, n, C] channel-last
     int64_t n[5];             // n[0] = T, n[i+1] = length after stage i
     int C[5];
     int B = 0, T = 0;

@@ -3,8 +3,9 @@
 // Replaces reference third_party/BigVGAN/models.py:207-238 (BigVGAN.forward), :103-121
 // (AMPBlock1.forward), activations.py:107-120 (SnakeBeta) with weight-norm folded at load.
 //
-// Data flow (per utterance, n_0 = T mel frames, n_{i+1} = u_i (n_i + 1)):
-//   conv_pre      : one GEMM over 7 contiguous channel-last mel frames -> [T, 128] channel-last
+// Data flow (per utterance, n_0 = T mel frames, n_{i+1} = u_i (n_i + 1)); every intermediate in HBM
+// is channel-last [B, n, C]:
+//   conv_pre      : one GEMM over 7 contiguous channel-last mel frames -> [T, 128]
 //   stage i (x4)  : one kernel per resblock kernel size k in {3,7,11}.  A CTA owns a time tile of the
 //                   stage's output rate plus a left halo of 12 (k-1) samples, and keeps the whole
 //                   chain  ConvTranspose1d -> 3 x (snake, dilated conv, snake, conv, residual)
@@ -13,6 +14,15 @@
 //                   partial tensors; their mean (models.py:219-225) is taken by the consumer on load.
 //   post          : mean -> snake -> conv_post(k=7) -> tanh -> / SCALING -> [:length]
 // Causal left padding is implicit: every conv input at global time < 0 is zero (models.py:110,117).
+//
+// Two arithmetic paths for the stage kernel:
+//   precision 0  fp32 FFMA, activations [C][time] in shared memory
+//   precision 1  tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate), implicit GEMM with
+//                M = time, N = C_out, K = taps x C_in.  Conv inputs live in shared memory as split
+//                bf16 (hi, lo) rows [time][C]; a tap is a row offset of the A fragment, so no im2col
+//                copy exists.  x.w ~= x_hi.w_hi + x_hi.w_lo + x_lo.w_hi.  The residual stream stays fp32.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace bvc {
@@ -37,6 +47,37 @@ __global__ void pad_mel_kernel(const float* __restrict__ mel, float* __restrict_
     out[idx] = t >= 0 ? mel[(b * T + t) * X + c] : 0.f;
 }
 
+struct StageArgs {
+    // stage input: n_parts channel-last tensors [B, rows, CIN] whose mean is the input (1 for conv_pre's output)
+    const float* in_p[3];
+    int n_parts;
+    long long in_bstride;     // floats per utterance
+    int n_in;
+    int n_out;
+    const float* w_up;        // fp32 [tap][ci][co]
+    const float* b_up;
+    const uint2* upf_h;       // fragment-packed per phase
+    const uint2* upf_l;
+    const float* w1[3];
+    const float* b1[3];
+    const float* w2[3];
+    const float* b2[3];
+    const uint2 *f1h[3], *f1l[3], *f2h[3], *f2l[3];
+    const float* ea[6];
+    const float* ieb[6];
+    int dil[3];
+    float* out;               // [B, n_out, C] channel-last
+    int TT;
+};
+
+__device__ __forceinline__ float load_mean(const StageArgs& a, size_t o) {
+    if (a.n_parts == 1) return __ldg(a.in_p[0] + o);
+    return ((__ldg(a.in_p[0] + o) + __ldg(a.in_p[1] + o)) + __ldg(a.in_p[2] + o)) / 3.0f;
+}
+
+// ===========================================================================
+// precision 0: fp32 FFMA stage kernel
+// ===========================================================================
 // in [C][WP] (conv input, already activated and zero where global time < 0)
 // w  [ci][tap][co], out positions p in [p_begin, W).  f(co, p, value) consumes the result.
 template <int C, int K, typename F>
@@ -87,28 +128,8 @@ __device__ __forceinline__ void conv_layer(const float* __restrict__ in, int WP,
     }
 }
 
-struct StageArgs {
-    // input: either channel-last single tensor (stage 0) or three channel-first partials
-    const float* in_cl;       // [B, rows_per_b, Cin] channel-last, or null
-    long long in_cl_bstride;  // floats per utterance
-    const float* in_p[3];     // [B, Cin, n_in]
-    int n_in;
-    int n_out;
-    const float* w_up;        // [tap][ci][co]
-    const float* b_up;
-    const float* w1[3];
-    const float* b1[3];
-    const float* w2[3];
-    const float* b2[3];
-    const float* ea[6];
-    const float* ieb[6];
-    int dil[3];
-    float* out;               // [B, C, n_out]
-    int TT;
-};
-
 template <int C, int U, int K>
-__global__ void __launch_bounds__(kThreads, 1) stage_kernel(StageArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) stage_fp32_kernel(StageArgs a) {
     constexpr int CIN = 2 * C;
     constexpr int HALO = 12 * (K - 1);
     extern __shared__ __align__(16) float smem[];
@@ -128,30 +149,17 @@ __global__ void __launch_bounds__(kThreads, 1) stage_kernel(StageArgs a) {
     const int tg0 = t0 - HALO;               // global time of position 0 (multiple of U)
     const int j_base = tg0 / U - 1;          // xin[.][0] <-> input sample j_base (exact: tg0 % U == 0)
 
-    // ---- load the stage input tile (mean of the producer's three resblock partials) ----
-    if (a.in_cl) {
-        const float* src = a.in_cl + (size_t)b * a.in_cl_bstride;
+    {
+        const size_t boff = (size_t)b * a.in_bstride;
         for (int i = tid; i < NJ * CIN; i += kThreads) {
             const int jj = i / CIN, ci = i - jj * CIN;
             const int j = j_base + jj;
-            xin[ci * NJP + jj] = (j >= 0 && j < a.n_in) ? __ldg(src + (size_t)j * CIN + ci) : 0.f;
-        }
-    } else {
-        const size_t boff = (size_t)b * CIN * a.n_in;
-        for (int i = tid; i < NJ * CIN; i += kThreads) {
-            const int ci = i / NJ, jj = i - ci * NJ;
-            const int j = j_base + jj;
-            float v = 0.f;
-            if (j >= 0 && j < a.n_in) {
-                const size_t o = boff + (size_t)ci * a.n_in + j;
-                v = ((__ldg(a.in_p[0] + o) + __ldg(a.in_p[1] + o)) + __ldg(a.in_p[2] + o)) / 3.0f;
-            }
-            xin[ci * NJP + jj] = v;
+            xin[ci * NJP + jj] = (j >= 0 && j < a.n_in) ? load_mean(a, boff + (size_t)j * CIN + ci) : 0.f;
         }
     }
     __syncthreads();
 
-    // ---- ConvTranspose1d(k = 2U, stride U): y[co, U j + r] = b + sum_ci x[ci,j] W[ci,co,r] + x[ci,j-1] W[ci,co,r+U]
+    // ConvTranspose1d(k = 2U, stride U): y[co, U j + r] = b + sum_ci x[ci,j] W[ci,co,r] + x[ci,j-1] W[ci,co,r+U]
     {
         constexpr int CG = C < 8 ? C : 8;
         constexpr int NCG = C / CG;
@@ -181,7 +189,6 @@ __global__ void __launch_bounds__(kThreads, 1) stage_kernel(StageArgs a) {
     }
     __syncthreads();   // xin (aliasing s1/s2) is dead from here on
 
-    // ---- AMP block: 3 x (snake -> dilated conv -> snake -> conv -> residual) ----
     int lo = 0;
 #pragma unroll 1
     for (int l = 0; l < 3; ++l) {
@@ -213,17 +220,245 @@ __global__ void __launch_bounds__(kThreads, 1) stage_kernel(StageArgs a) {
         lo = lo2;
     }
 
-    // ---- write the tile (positions [HALO, W)) ----
-    float* dst = a.out + (size_t)b * C * a.n_out;
+    float* dst = a.out + (size_t)b * a.n_out * C;
     for (int i = tid; i < C * TT; i += kThreads) {
-        const int c = i / TT, tt = i - c * TT;
+        const int tt = i / C, c = i - tt * C;
         const int tg = t0 + tt;
-        if (tg < a.n_out) dst[(size_t)c * a.n_out + tg] = cur[c * WP + HALO + tt];
+        if (tg < a.n_out) dst[(size_t)tg * C + c] = cur[c * WP + HALO + tt];
+    }
+}
+
+// ===========================================================================
+// precision 1: tensor-core stage kernel
+// ===========================================================================
+template <int C>
+struct RowLayout {
+    static constexpr int PW = C >= 16 ? C / 2 + 4 : C / 2;   // uint32 (bf16 pair) words per activation row
+    static constexpr int PF = C + 8;                         // floats per residual row
+};
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint2& b) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+// One warp computes a 32-row x COUT tile of  out[row][co] = sum_{tap,ci} in[row - (NTAPS-1-tap) d][ci] W[tap][ci][co].
+// inh/inl: split-bf16 activation rows (pitch RowLayout<CIN>::PW words); rows are clamped to [0, max_row].
+// wh/wl: fragment-packed weights.  epi(row, co, v0, v1) receives channels (co, co+1) of one row.
+template <int CIN, int COUT, int NTAPS, typename Epi>
+__device__ __forceinline__ void mma_tile32(const uint32_t* __restrict__ inh, const uint32_t* __restrict__ inl,
+                                           int max_row, const uint2* __restrict__ wh, const uint2* __restrict__ wl,
+                                           int d, int r0, Epi epi) {
+    constexpr int PW = RowLayout<CIN>::PW;
+    constexpr int NT = COUT / 8;
+    constexpr int KC = (NTAPS * CIN + 15) / 16;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+
+#pragma unroll 2
+    for (int kc = 0; kc < KC; ++kc) {
+        const int k_lo = 16 * kc + 2 * q, k_hi = k_lo + 8;
+        const int tap_lo = k_lo / CIN, tap_hi = k_hi / CIN;
+        const int w_lo = (k_lo % CIN) >> 1, w_hi = (k_hi % CIN) >> 1;
+        const int off_lo = tap_lo < NTAPS ? (NTAPS - 1 - tap_lo) * d : 0;
+        const int off_hi = tap_hi < NTAPS ? (NTAPS - 1 - tap_hi) * d : 0;
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int ra = r0 + mt * 16 + g, rb = ra + 8;
+            const int i0 = min(ra - off_lo, max_row) * PW + w_lo, i1 = min(rb - off_lo, max_row) * PW + w_lo;
+            const int i2 = min(ra - off_hi, max_row) * PW + w_hi, i3 = min(rb - off_hi, max_row) * PW + w_hi;
+            ah[mt][0] = inh[i0]; ah[mt][1] = inh[i1]; ah[mt][2] = inh[i2]; ah[mt][3] = inh[i3];
+            al[mt][0] = inl[i0]; al[mt][1] = inl[i1]; al[mt][2] = inl[i2]; al[mt][3] = inl[i3];
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const uint2 bh = __ldg(wh + (kc * NT + nt) * 32 + lane);
+            const uint2 bl = __ldg(wl + (kc * NT + nt) * 32 + lane);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                mma16816(acc[mt][nt], al[mt], bh);
+                mma16816(acc[mt][nt], ah[mt], bl);
+                mma16816(acc[mt][nt], ah[mt], bh);
+            }
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int row = r0 + mt * 16 + g, co = nt * 8 + 2 * q;
+            epi(row, co, acc[mt][nt][0], acc[mt][nt][1]);
+            epi(row + 8, co, acc[mt][nt][2], acc[mt][nt][3]);
+        }
+}
+
+template <int C, int U, int K>
+__global__ void __launch_bounds__(kThreads, 1) stage_mma_kernel(StageArgs a) {
+    constexpr int CIN = 2 * C;
+    constexpr int HALO = 12 * (K - 1);
+    constexpr int PW = RowLayout<C>::PW, PF = RowLayout<C>::PF, PWI = RowLayout<CIN>::PW;
+    extern __shared__ __align__(16) float smem[];
+    const int TT = a.TT;
+    const int W = TT + HALO;
+    float* cur = smem;                                            // [W][PF] fp32 residual stream
+    uint32_t* s1h = reinterpret_cast<uint32_t*>(cur + W * PF);    // [W][PW] conv1 input (hi)
+    uint32_t* s1l = s1h + W * PW;
+    uint32_t* s2h = s1l + W * PW;                                 // [W][PW] conv2 input
+    uint32_t* s2l = s2h + W * PW;
+    const int NJ = W / U + 2;
+    uint32_t* xh = s1h;                                           // [NJ][PWI] stage input tile (aliases s1/s2)
+    uint32_t* xl = xh + NJ * PWI;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * TT;
+    const int tg0 = t0 - HALO;
+    const int j_base = tg0 / U - 1;
+
+    // ---- stage input tile: mean of the producer's partials, split to bf16 hi/lo ----
+    {
+        const size_t boff = (size_t)b * a.in_bstride;
+        constexpr int V = CIN / 4;
+        for (int i = tid; i < NJ * V; i += kThreads) {
+            const int jj = i / V, c4 = i - jj * V;
+            const int j = j_base + jj;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j >= 0 && j < a.n_in) {
+                const size_t o = boff + (size_t)j * CIN + c4 * 4;
+                v = __ldg(reinterpret_cast<const float4*>(a.in_p[0] + o));
+                if (a.n_parts == 3) {
+                    const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.in_p[1] + o));
+                    const float4 v2 = __ldg(reinterpret_cast<const float4*>(a.in_p[2] + o));
+                    v.x = ((v.x + v1.x) + v2.x) / 3.0f; v.y = ((v.y + v1.y) + v2.y) / 3.0f;
+                    v.z = ((v.z + v1.z) + v2.z) / 3.0f; v.w = ((v.w + v1.w) + v2.w) / 3.0f;
+                }
+            }
+            uint32_t h0, l0, h1, l1;
+            split_pair(v.x, v.y, h0, l0);
+            split_pair(v.z, v.w, h1, l1);
+            *reinterpret_cast<uint2*>(xh + jj * PWI + c4 * 2) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(xl + jj * PWI + c4 * 2) = make_uint2(l0, l1);
+        }
+    }
+    __syncthreads();
+
+    // ---- ConvTranspose1d as U phase convolutions: phase r is a 2-tap conv over (x[j-1], x[j]) ----
+    {
+        constexpr int KC_UP = (2 * CIN) / 16, NT = C / 8;
+        const int rows = W / U;                      // low-rate rows m in [0, rows): output position p = U m + r
+        const int tiles = (rows + 31) / 32;
+        for (int item = warp; item < U * tiles; item += kThreads / 32) {
+            const int r = item / tiles, tile = item - r * tiles;
+            const uint2* wh = a.upf_h + (size_t)r * KC_UP * NT * 32;
+            const uint2* wl = a.upf_l + (size_t)r * KC_UP * NT * 32;
+            mma_tile32<CIN, C, 2>(xh, xl, NJ - 1, wh, wl, 1, 1 + tile * 32, [&](int row, int co, float v0, float v1) {
+                const int p = U * (row - 1) + r;
+                if (row - 1 < rows)
+                    *reinterpret_cast<float2*>(cur + p * PF + co) =
+                        make_float2(v0 + __ldg(a.b_up + co), v1 + __ldg(a.b_up + co + 1));
+            });
+        }
+    }
+    __syncthreads();   // xh/xl are dead from here on
+
+    // ---- AMP block ----
+    int lo = 0;
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {
+        const int d = a.dil[l];
+        {
+            const float* ea = a.ea[2 * l];
+            const float* ieb = a.ieb[2 * l];
+            constexpr int CP = C / 2;
+            for (int i = tid; i < (W - lo) * CP; i += kThreads) {
+                const int row = lo + i / CP, cp = i % CP;
+                const float2 v = *reinterpret_cast<const float2*>(cur + row * PF + 2 * cp);
+                float y0 = 0.f, y1 = 0.f;
+                if (tg0 + row >= 0) {
+                    y0 = snake(v.x, __ldg(ea + 2 * cp), __ldg(ieb + 2 * cp));
+                    y1 = snake(v.y, __ldg(ea + 2 * cp + 1), __ldg(ieb + 2 * cp + 1));
+                }
+                uint32_t hi, lw;
+                split_pair(y0, y1, hi, lw);
+                s1h[row * PW + cp] = hi;
+                s1l[row * PW + cp] = lw;
+            }
+        }
+        __syncthreads();
+        const int lo1 = lo + (K - 1) * d;
+        {
+            const float* ea = a.ea[2 * l + 1];
+            const float* ieb = a.ieb[2 * l + 1];
+            const float* bias = a.b1[l];
+            const int tiles = (W - lo1 + 31) / 32;
+            for (int tile = warp; tile < tiles; tile += kThreads / 32) {
+                mma_tile32<C, C, K>(s1h, s1l, W - 1, a.f1h[l], a.f1l[l], d, lo1 + tile * 32,
+                                    [&](int row, int co, float v0, float v1) {
+                                        if (row >= W) return;
+                                        float y0 = 0.f, y1 = 0.f;
+                                        if (tg0 + row >= 0) {
+                                            y0 = snake(v0 + __ldg(bias + co), __ldg(ea + co), __ldg(ieb + co));
+                                            y1 = snake(v1 + __ldg(bias + co + 1), __ldg(ea + co + 1), __ldg(ieb + co + 1));
+                                        }
+                                        uint32_t hi, lw;
+                                        split_pair(y0, y1, hi, lw);
+                                        s2h[row * PW + (co >> 1)] = hi;
+                                        s2l[row * PW + (co >> 1)] = lw;
+                                    });
+            }
+        }
+        __syncthreads();
+        const int lo2 = lo1 + (K - 1);
+        {
+            const float* bias = a.b2[l];
+            const int tiles = (W - lo2 + 31) / 32;
+            for (int tile = warp; tile < tiles; tile += kThreads / 32) {
+                mma_tile32<C, C, K>(s2h, s2l, W - 1, a.f2h[l], a.f2l[l], 1, lo2 + tile * 32,
+                                    [&](int row, int co, float v0, float v1) {
+                                        if (row >= W) return;
+                                        float2* p = reinterpret_cast<float2*>(cur + row * PF + co);
+                                        float2 c = *p;
+                                        c.x += v0 + __ldg(bias + co);
+                                        c.y += v1 + __ldg(bias + co + 1);
+                                        *p = c;
+                                    });
+            }
+        }
+        __syncthreads();
+        lo = lo2;
+    }
+
+    // ---- write the tile (rows [HALO, W)), channel-last, coalesced ----
+    float* dst = a.out + (size_t)b * a.n_out * C;
+    constexpr int V = C / 4;
+    for (int i = tid; i < TT * V; i += kThreads) {
+        const int tt = i / V, c4 = i - tt * V;
+        const int tg = t0 + tt;
+        if (tg < a.n_out)
+            *reinterpret_cast<float4*>(dst + (size_t)tg * C + c4 * 4) =
+                *reinterpret_cast<const float4*>(cur + (HALO + tt) * PF + c4 * 4);
     }
 }
 
 struct PostArgs {
-    const float* in_p[3];   // [B, C, n]
+    const float* in_p[3];   // [B, n, C] channel-last
     int n;
     int n_out;              // min(length, n)
     const float* ea;
@@ -241,13 +476,13 @@ __global__ void __launch_bounds__(kThreads) post_kernel(PostArgs a) {
     __shared__ float w[C * K];
     const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * TT;
     if (tid < C * K) w[tid] = a.w[tid];
-    const size_t boff = (size_t)b * C * a.n;
+    const size_t boff = (size_t)b * a.n * C;
     for (int i = tid; i < C * (TT + K - 1); i += kThreads) {
-        const int c = i / (TT + K - 1), p = i - c * (TT + K - 1);
+        const int p = i / C, c = i - p * C;
         const int tg = t0 - (K - 1) + p;
         float v = 0.f;
         if (tg >= 0 && tg < a.n) {
-            const size_t o = boff + (size_t)c * a.n + tg;
+            const size_t o = boff + (size_t)tg * C + c;
             const float x = ((__ldg(a.in_p[0] + o) + __ldg(a.in_p[1] + o)) + __ldg(a.in_p[2] + o)) / 3.0f;
             v = snake(x, __ldg(a.ea + c), __ldg(a.ieb + c));
         }
@@ -268,27 +503,38 @@ __global__ void __launch_bounds__(kThreads) post_kernel(PostArgs a) {
 }
 
 template <int C, int U, int K>
-int launch_stage(const StageArgs& a, int B, cudaStream_t stream) {
+int launch_stage(const StageArgs& a, int B, int precision, cudaStream_t stream) {
     constexpr int HALO = 12 * (K - 1);
-    const int WP = a.TT + HALO + 4;
-    const size_t smem = (size_t)3 * C * WP * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        BVC_CUDA(cudaFuncSetAttribute(stage_kernel<C, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
     dim3 grid((a.n_out + a.TT - 1) / a.TT, B);
-    stage_kernel<C, U, K><<<grid, kThreads, smem, stream>>>(a);
+    if (precision == 1) {
+        const int W = a.TT + HALO;
+        const size_t smem = (size_t)W * (RowLayout<C>::PF * 4 + 4 * RowLayout<C>::PW * 4);
+        static bool attr_set = false;
+        if (!attr_set) {
+            BVC_CUDA(cudaFuncSetAttribute(stage_mma_kernel<C, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            attr_set = true;
+        }
+        stage_mma_kernel<C, U, K><<<grid, kThreads, smem, stream>>>(a);
+    } else {
+        const int WP = a.TT + HALO + 4;
+        const size_t smem = (size_t)3 * C * WP * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            BVC_CUDA(cudaFuncSetAttribute(stage_fp32_kernel<C, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            attr_set = true;
+        }
+        stage_fp32_kernel<C, U, K><<<grid, kThreads, smem, stream>>>(a);
+    }
     BVC_CHECK_LAUNCH();
     return BVC_OK;
 }
 
 template <int C, int U>
-int launch_stage_k(int k, const StageArgs& a, int B, cudaStream_t stream) {
+int launch_stage_k(int k, const StageArgs& a, int B, int precision, cudaStream_t stream) {
     switch (k) {
-        case 3: return launch_stage<C, U, 3>(a, B, stream);
-        case 7: return launch_stage<C, U, 7>(a, B, stream);
-        case 11: return launch_stage<C, U, 11>(a, B, stream);
+        case 3: return launch_stage<C, U, 3>(a, B, precision, stream);
+        case 7: return launch_stage<C, U, 7>(a, B, precision, stream);
+        case 11: return launch_stage<C, U, 11>(a, B, precision, stream);
     }
     set_error("unsupported resblock kernel size (build covers 3, 7, 11)");
     return BVC_ERR_INVALID;
@@ -349,21 +595,25 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
             const AmpBlockWeights& bw = w.blocks[i * 3 + j];
             StageArgs a;
             if (i == 0) {
-                a.in_cl = vb.pre;
-                a.in_cl_bstride = (long long)(T + 6) * w.c0;
-                a.in_p[0] = a.in_p[1] = a.in_p[2] = nullptr;
+                a.n_parts = 1;
+                a.in_p[0] = a.in_p[1] = a.in_p[2] = vb.pre;
+                a.in_bstride = (long long)(T + 6) * w.c0;
             } else {
-                a.in_cl = nullptr;
-                a.in_cl_bstride = 0;
+                a.n_parts = 3;
                 for (int q = 0; q < 3; ++q) a.in_p[q] = vb.part[i - 1][q];
+                a.in_bstride = (long long)vb.n[i] * vb.C[i];
             }
             a.n_in = (int)vb.n[i];
             a.n_out = (int)vb.n[i + 1];
             a.w_up = w.w_up[i];
             a.b_up = w.b_up[i];
+            a.upf_h = w.upf_h[i];
+            a.upf_l = w.upf_l[i];
             for (int l = 0; l < 3; ++l) {
                 a.w1[l] = bw.w1[l]; a.b1[l] = bw.b1[l];
                 a.w2[l] = bw.w2[l]; a.b2[l] = bw.b2[l];
+                a.f1h[l] = bw.f1h[l]; a.f1l[l] = bw.f1l[l];
+                a.f2h[l] = bw.f2h[l]; a.f2l[l] = bw.f2l[l];
                 a.dil[l] = w.dil[l];
             }
             for (int q = 0; q < 6; ++q) { a.ea[q] = bw.act[q].ea; a.ieb[q] = bw.act[q].inv_eb; }
@@ -371,10 +621,10 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
             a.TT = kTT[i];
             int rc;
             switch (i) {
-                case 0: rc = launch_stage_k<64, 8>(bw.k, a, B, stream); break;
-                case 1: rc = launch_stage_k<32, 8>(bw.k, a, B, stream); break;
-                case 2: rc = launch_stage_k<16, 2>(bw.k, a, B, stream); break;
-                default: rc = launch_stage_k<8, 2>(bw.k, a, B, stream); break;
+                case 0: rc = launch_stage_k<64, 8>(bw.k, a, B, precision, stream); break;
+                case 1: rc = launch_stage_k<32, 8>(bw.k, a, B, precision, stream); break;
+                case 2: rc = launch_stage_k<16, 2>(bw.k, a, B, precision, stream); break;
+                default: rc = launch_stage_k<8, 2>(bw.k, a, B, precision, stream); break;
             }
             if (rc != BVC_OK) return rc;
         }

@@ -146,7 +146,7 @@ int64_t bvc_kernel_launches(const bvc_handle* h);
 int bvc_set_precision(bvc_handle* h, int32_t mode);
 
 /* Debug/parity taps: copy an internal device buffer of the LAST call to host.
- * Names: "voc_pre" [B,T+6,128] channel-last, "voc_stage{0..3}_{0..2}" [B,C,n] partial sums.
+ * Names: "voc_pre" [B,T+6,128] channel-last, "voc_stage{0..3}_{0..2}" [B,n,C] channel-last partial sums.
  * Synchronises the device. */
 int bvc_debug_read(bvc_handle* h, const char* name, float* dst_host, size_t n_floats);
 

@@ -54,8 +54,9 @@ def stage_report(model, oracle, x, bitrate, vocoder_taps=True):
         out["voc_pre_maxabs"] = float((pre - o_taps2["pre"]).abs().max())
         for i in range(4):
             ref = o_taps2[f"stage{i}"]
-            parts = [model._engine.debug_read(f"voc_stage{i}_{j}", tuple(ref.shape)) for j in range(3)]
-            got = ((parts[0] + parts[1]) + parts[2]) / 3.0
+            shp = (ref.shape[0], ref.shape[2], ref.shape[1])          # partials are channel-last [B, n, C]
+            parts = [model._engine.debug_read(f"voc_stage{i}_{j}", shp) for j in range(3)]
+            got = (((parts[0] + parts[1]) + parts[2]) / 3.0).permute(0, 2, 1)
             out[f"voc_stage{i}_maxabs"] = float((got - ref).abs().max())
             out[f"voc_stage{i}_refmax"] = float(ref.abs().max())
     out["voc_wav_maxabs"] = float((wav_from_oracle_mel - o_wav).abs().max())
