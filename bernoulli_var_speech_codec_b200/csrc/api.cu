@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "recurrent.cuh"
 
 namespace bvc {
 
@@ -103,6 +104,41 @@ bool make_linear(bvc_handle* h, const std::vector<float>& w, int N, int K, Linea
         if (!out->w_hi || !out->w_lo) return false;
     }
     return true;
+}
+
+// split-bf16 copy [N][Kpad] (zero padded along K) for the persistent recurrent kernel
+bool make_split(bvc_handle* h, const std::vector<float>& w, int N, int K, int Kpad, SplitW* out) {
+    std::vector<uint16_t> hi((size_t)N * Kpad, 0), lo((size_t)N * Kpad, 0);
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+            const float v = w[(size_t)n * K + k];
+            const uint16_t vh = f2bf(v);
+            hi[(size_t)n * Kpad + k] = vh;
+            lo[(size_t)n * Kpad + k] = f2bf(v - bf2f(vh));
+        }
+    out->hi = reinterpret_cast<const __nv_bfloat16*>(dev_upload(h, hi));
+    out->lo = reinterpret_cast<const __nv_bfloat16*>(dev_upload(h, lo));
+    out->N = N;
+    out->K = Kpad;
+    return out->hi && out->lo;
+}
+SplitW alias_split(const LinearWeights& lw) {
+    SplitW s;
+    s.hi = reinterpret_cast<const __nv_bfloat16*>(lw.w_hi);
+    s.lo = reinterpret_cast<const __nv_bfloat16*>(lw.w_lo);
+    s.N = lw.N;
+    s.K = lw.K;
+    return s;
+}
+// GRU gate interleave: natural row gate*H + j  ->  24 (j / 8) + 8 gate + (j % 8), so that a 24-column
+// group holds r, z, n of 8 hidden units (recurrent.cu, KIND_GRU epilogue)
+std::vector<float> gate_interleave_rows(const std::vector<float>& w, int H, int K) {
+    std::vector<float> out(w.size());
+    for (int gate = 0; gate < 3; ++gate)
+        for (int j = 0; j < H; ++j)
+            memcpy(&out[(size_t)(24 * (j / 8) + 8 * gate + (j % 8)) * K], &w[(size_t)(gate * H + j) * K],
+                   sizeof(float) * K);
+    return out;
 }
 
 int collect(const bvc_tensor* tensors, int n, TensorMap* m) {
@@ -311,6 +347,7 @@ int bvc_destroy(bvc_handle* h) {
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->ws_event) cudaEventDestroy(h->ws_event);
+    if (h->bw.rw.prog_host) cudaFreeHost(h->bw.rw.prog_host);
     cudaSetDevice(prev);
     delete h;
     return BVC_OK;
@@ -393,6 +430,42 @@ int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
         w.b_zcat = up(b);
     }
     ok = ok && make_linear(h, slice(wih, 0, 3 * H, 0, H), (int)(3 * H), (int)H, &w.ihx);
+    {   // persistent recurrent kernel operands
+        RecurrentWeights& rw = w.rw;
+        const int Hi = (int)H, Xi = (int)X;
+        ok = ok && make_split(h, slice(e0, 0, H, H, 2 * H), Hi, Hi, Hi, &rw.e0h);
+        ok = ok && make_split(h, slice(d0, 0, H, H, 2 * H), Hi, Hi, Hi, &rw.d0h);
+        ok = ok && make_split(h, slice(d0, 0, H, 0, H), Hi, Hi, Hi, &rw.d0z);
+        ok = ok && make_split(h, gate_interleave_rows(to_vec(whh), Hi, Hi), 3 * Hi, Hi, Hi, &rw.whh_p);
+        const std::vector<float> ihz_p = gate_interleave_rows(slice(wih, 0, 3 * H, H, 2 * H), Hi, Hi);
+        ok = ok && make_split(h, ihz_p, 3 * Hi, Hi, Hi, &rw.ihz_p);
+        ok = ok && make_split(h, gate_interleave_rows(slice(wih, 0, 3 * H, 0, H), Hi, Hi), 3 * Hi, Hi, Hi, &rw.ihx_p);
+        ok = ok && make_split(h, to_vec(m["phi_x.0.weight"]), Hi, Xi, ((Xi + 63) / 64) * 64, &rw.px0p);
+        rw.e2 = alias_split(w.e2); rw.e4 = alias_split(w.e4);
+        rw.pz0 = alias_split(w.pz0); rw.pz2 = alias_split(w.pz2); rw.pz4 = alias_split(w.pz4);
+        rw.d2 = alias_split(w.d2); rw.d4 = alias_split(w.d4); rw.d6 = alias_split(w.d6);
+        rw.px2 = alias_split(w.px2); rw.px4 = alias_split(w.px4);
+        rw.b_e0 = up(to_vec(m["enc.0.bias"]));
+        rw.b_d0 = up(to_vec(m["dec.0.bias"]));
+        const std::vector<float> bih_p = gate_interleave_rows(to_vec(m["rnn.bias_ih_l0"]), Hi, 1);
+        rw.b_hh_p = up(gate_interleave_rows(to_vec(m["rnn.bias_hh_l0"]), Hi, 1));
+        rw.b_ih_p = up(bih_p);
+        std::vector<float> zc = slice(d0, 0, H, 0, H);
+        append(zc, ihz_p);
+        ok = ok && make_linear(h, zc, 4 * Hi, Hi, &rw.zcat_p);
+        std::vector<float> bz = to_vec(m["dec.0.bias"]);
+        append(bz, bih_p);
+        rw.b_zcat_p = up(bz);
+        void* p1 = nullptr; void* p2 = nullptr; void* p3 = nullptr;
+        ok = ok && cudaMalloc(&p1, 16) == cudaSuccess && cudaMalloc(&p2, sizeof(rec::Program)) == cudaSuccess &&
+             cudaMallocHost(&p3, sizeof(rec::Program)) == cudaSuccess;
+        if (p1) h->allocs.push_back(p1);
+        if (p2) h->allocs.push_back(p2);
+        rw.sync_words = (unsigned*)p1;
+        rw.prog_dev = (rec::Program*)p2;
+        rw.prog_host = (rec::Program*)p3;
+        rw.ready = ok && (H % 64 == 0) && (Z % 64 == 0) && X <= 128;
+    }
     REQUIRE(ok, BVC_ERR_NOMEM, "device allocation failed while loading BVRNN weights");
     h->have_bvrnn = true;
     return BVC_OK;

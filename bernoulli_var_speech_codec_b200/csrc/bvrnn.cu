@@ -10,7 +10,13 @@
 // ([enc.0_h; dec.0_h; W_hh] . h), and the layers that read phi_z likewise
 // ([dec.0_z; W_ih_z] . phi_z), so a frame is 13 (encode) / 8 (decode) dependent GEMMs
 // plus the Bernoulli bottleneck and the GRU gate kernel.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
+#include "recurrent.cuh"
 
 namespace bvc {
 
@@ -103,11 +109,11 @@ size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T) {
     n += BT * w.X + 64;                 // normalised mel
     n += 2 * (BT * H + 64);             // two hoisted activation buffers
     n += BT * 4 * H + 64;               // decode: hoisted [dec.0_z ; W_ih_z] . phi_z
-    n += (size_t)B * (28 * H + 2 * w.X + 2 * w.Z) + 64 * 32;
+    n += (size_t)B * (40 * H + 2 * w.X + 2 * w.Z + 256) + 64 * 64;
     return n;
 }
 
-int bvrnn_encode(const BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
+static int bvrnn_encode_layers(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
                  float* all_h, float* h_final, int precision, cudaStream_t s) {
     const int H = w.H, X = w.X, Z = w.Z;
@@ -193,7 +199,7 @@ int bvrnn_encode(const BvrnnWeights& w, Workspace& ws, const float* mel, const f
     return BVC_OK;
 }
 
-int bvrnn_decode(const BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T,
+static int bvrnn_decode_layers(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T,
                  float* mel, float* h_final, int precision, cudaStream_t s) {
     const int H = w.H, X = w.X, Z = w.Z;
     const size_t BT = (size_t)B * T;
@@ -249,6 +255,304 @@ int bvrnn_decode(const BvrnnWeights& w, Workspace& ws, const float* codes, const
     }
     if (h_final) BVC_CUDA(cudaMemcpyAsync(h_final, hc, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, s));
     return BVC_OK;
+}
+
+
+// =============================================================================================
+// Persistent-kernel path (precision 1): host-side program builder and scheduler
+// =============================================================================================
+namespace {
+
+struct BgWork {
+    int op, first_phase, last_phase, n_tiles, next_tile;
+};
+
+struct ProgramBuilder {
+    rec::Program* p;
+    int G, M;
+    std::vector<std::vector<int>> crit;   // per phase: critical op indices
+    std::vector<BgWork> bg;
+
+    int tiles_of(const rec::Op& op) const {
+        const int bn = 32 * op.ni;
+        return ((M + 31) / 32) * ((op.N + bn - 1) / bn);
+    }
+    double cost_of(const rec::Op& op) const { return (double)op.K * (32 + 32 * op.ni) / (1024.0 * 96.0); }
+
+    int add_op(const rec::Op& op) {
+        p->ops[p->n_ops] = op;
+        return p->n_ops++;
+    }
+
+    // Greedy list scheduler: critical tiles round-robin over the CTAs; background tiles fill the slack of a
+    // phase (earliest deadline first) and whatever is left at an op's deadline is spread over the least-loaded CTAs.
+    bool schedule() {
+        const int n_ph = (int)crit.size();
+        p->n_phases = n_ph;
+        p->grid = G;
+        int n_list = 0;
+        std::vector<std::vector<uint32_t>> lists(G);
+        std::vector<double> load(G);
+        const double full = 1.0;
+        for (int ph = 0; ph < n_ph; ++ph) {
+            for (auto& l : lists) l.clear();
+            std::fill(load.begin(), load.end(), 0.0);
+            int rr = 0;
+            for (int oi : crit[ph]) {
+                const int nt = tiles_of(p->ops[oi]);
+                const double c = cost_of(p->ops[oi]);
+                for (int t = 0; t < nt; ++t) {
+                    lists[rr].push_back(((uint32_t)oi << 20) | (uint32_t)t);
+                    load[rr] += c;
+                    rr = (rr + 1) % G;
+                }
+            }
+            double lmax = *std::max_element(load.begin(), load.end());
+            if (lmax < full) lmax = full;
+            std::vector<BgWork*> ready;
+            for (auto& b : bg)
+                if (b.first_phase <= ph && ph <= b.last_phase && b.next_tile < b.n_tiles) ready.push_back(&b);
+            std::sort(ready.begin(), ready.end(), [](BgWork* a, BgWork* b) { return a->last_phase < b->last_phase; });
+            for (BgWork* b : ready) {
+                const double c = cost_of(p->ops[b->op]);
+                const bool deadline = (b->last_phase == ph);
+                while (b->next_tile < b->n_tiles) {
+                    const int cta = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                    if (!deadline && load[cta] + c > lmax + 1e-9) break;
+                    lists[cta].push_back(((uint32_t)b->op << 20) | (uint32_t)b->next_tile++);
+                    load[cta] += c;
+                }
+            }
+            for (int c = 0; c < G; ++c) {
+                p->list_start[ph * G + c] = n_list;
+                for (uint32_t e : lists[c]) {
+                    if (n_list >= rec::MAX_TILES) return false;
+                    p->tiles[n_list++] = e;
+                }
+            }
+        }
+        p->list_start[n_ph * G] = n_list;
+        for (auto& b : bg)
+            if (b.next_tile < b.n_tiles) return false;
+        return true;
+    }
+};
+
+rec::Op linear_op(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int lda, const SplitW& w, const float* bias,
+                  int act, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldos) {
+    rec::Op o;
+    memset(&o, 0, sizeof(o));
+    o.a_hi = a_hi; o.a_lo = a_lo; o.lda = lda;
+    o.w_hi = w.hi; o.w_lo = w.lo; o.N = w.N; o.K = w.K;
+    o.bias = bias; o.act = act;
+    o.out_hi = out_hi; o.out_lo = out_lo; o.ldos = ldos;
+    o.ni = 2;
+    o.kind = rec::KIND_LINEAR;
+    return o;
+}
+
+struct SplitBuf {
+    __nv_bfloat16 *hi, *lo;
+};
+SplitBuf take_split(Workspace& ws, size_t n) {
+    SplitBuf b;
+    b.hi = reinterpret_cast<__nv_bfloat16*>(ws.take((n + 1) / 2));
+    b.lo = reinterpret_cast<__nv_bfloat16*>(ws.take((n + 1) / 2));
+    return b;
+}
+
+int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
+    if (!pb.schedule()) {
+        set_error("recurrent program does not fit the static limits (MAX_TILES)");
+        return BVC_ERR_INVALID;
+    }
+    // the pinned staging copy is reused by the next call: wait until the previous upload has been consumed
+    BVC_CUDA(cudaMemcpyAsync(w.rw.prog_dev, w.rw.prog_host, sizeof(rec::Program), cudaMemcpyHostToDevice, s));
+    int rc = rec::launch(w.rw.prog_dev, pb.G, w.rw.sync_words, s);
+    if (rc) return rc;
+    // prog_host is overwritten by the next call; the copy above must have been issued from a stable buffer
+    BVC_CUDA(cudaStreamSynchronize(s));
+    unsigned flags[2];
+    BVC_CUDA(cudaMemcpy(flags, w.rw.sync_words, sizeof(flags), cudaMemcpyDeviceToHost));
+    if (flags[1] != 0) {
+        set_error("recurrent kernel aborted: device-wide barrier timed out");
+        return BVC_ERR_DEVICE;
+    }
+    return BVC_OK;
+}
+
+}  // namespace
+
+static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits,
+                                   float bits_scalar, const float* h0, int B, int T, float* codes,
+                                   unsigned long long* packed, float* logits, float* all_h, float* h_final,
+                                   cudaStream_t s) {
+    const int H = w.H, X = w.X, Z = w.Z;
+    const size_t BT = (size_t)B * T;
+    RecurrentWeights& rw = w.rw;
+    int dev = 0, G = 0;
+    BVC_CUDA(cudaGetDevice(&dev));
+    BVC_TRY(rec::max_grid(dev, &G));
+    if (G > rec::MAX_GRID) G = rec::MAX_GRID;
+
+    float* yn = ws.take(BT * X);
+    float* PA = ws.take(BT * H);
+    float* PB = ws.take(BT * H);
+    float* hf = ws.take((size_t)B * H);
+    float* dh = ws.take((size_t)B * H);
+    float* gh = ws.take((size_t)B * 3 * H);
+    float* giz = ws.take((size_t)B * 3 * H);
+    const size_t BH = (size_t)B * H;
+    SplitBuf hS = take_split(ws, BH), e1S = take_split(ws, BH), e2S = take_split(ws, BH);
+    SplitBuf zS = take_split(ws, (size_t)B * Z), z1S = take_split(ws, BH), z2S = take_split(ws, BH);
+    SplitBuf pzS = take_split(ws, BH), d1S = take_split(ws, BH), d2S = take_split(ws, BH), d3S = take_split(ws, BH);
+    SplitBuf mnS = take_split(ws, (size_t)B * 128), x1S = take_split(ws, BH), x2S = take_split(ws, BH);
+    SplitBuf pxS = take_split(ws, BH);
+
+    // hoisted over all frames (large GEMMs): phi_x(yn), then enc.0[:, :H] . phi_x
+    {
+        const size_t n = BT * X;
+        normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mel, w.mean, w.std, yn, n, X);
+        BVC_CHECK_LAUNCH();
+    }
+    BVC_TRY(run_linear(yn, X, (int)BT, w.px0, w.b_px0, H, PA, H, 1, s));
+    BVC_TRY(run_linear(PA, H, (int)BT, w.px2, w.b_px2, H, PB, H, 1, s));
+    BVC_TRY(run_linear(PB, H, (int)BT, w.px4, w.b_px4, H, PA, H, 1, s));
+    BVC_TRY(run_linear(PA, H, (int)BT, w.e0x, nullptr, 0, PB, H, 1, s));
+    float* E0x = PB;
+    BVC_TRY(rec::init_state(h0, hf, hS.hi, hS.lo, (int)BH, mnS.hi, mnS.lo, B * 128, s));
+
+    rec::Program* p = rw.prog_host;
+    memset(p, 0, sizeof(rec::Program));
+    rec::Frame& fr = p->frame;
+    fr.M = B; fr.T = T; fr.X = X; fr.Z = Z; fr.H = H; fr.var_bit = w.var_bit;
+    fr.bits_scalar = bits_scalar; fr.bits = bits; fr.codes = codes; fr.packed = packed; fr.logits = logits;
+    fr.all_h = all_h; fr.h = hf; fr.gh = gh; fr.mean = w.mean; fr.std = w.std; fr.mel_out = nullptr;
+
+    ProgramBuilder pb;
+    pb.p = p; pb.G = G; pb.M = B;
+    rec::Op o;
+    o = linear_op(hS.hi, hS.lo, H, rw.e0h, rw.b_e0, 1, e1S.hi, e1S.lo, H);
+    o.addend = E0x; o.ldadd = T * H; o.add_tstride = H;
+    const int op_e1 = pb.add_op(o);
+    o = linear_op(hS.hi, hS.lo, H, rw.d0h, nullptr, 0, nullptr, nullptr, 0);
+    o.out_f = dh; o.ldo = H;
+    const int op_dh = pb.add_op(o);
+    o = linear_op(hS.hi, hS.lo, H, rw.whh_p, rw.b_hh_p, 0, nullptr, nullptr, 0);
+    o.out_f = gh; o.ldo = 3 * H;
+    const int op_gh = pb.add_op(o);
+    const int op_e2 = pb.add_op(linear_op(e1S.hi, e1S.lo, H, rw.e2, w.b_e2, 1, e2S.hi, e2S.lo, H));
+    o = linear_op(e2S.hi, e2S.lo, H, rw.e4, w.b_e4, 0, zS.hi, zS.lo, Z);
+    o.kind = rec::KIND_BOTTLENECK;
+    const int op_e4 = pb.add_op(o);
+    const int op_z1 = pb.add_op(linear_op(zS.hi, nullptr, Z, rw.pz0, w.b_pz0, 1, z1S.hi, z1S.lo, H));
+    const int op_z2 = pb.add_op(linear_op(z1S.hi, z1S.lo, H, rw.pz2, w.b_pz2, 1, z2S.hi, z2S.lo, H));
+    const int op_pz = pb.add_op(linear_op(z2S.hi, z2S.lo, H, rw.pz4, w.b_pz4, 1, pzS.hi, pzS.lo, H));
+    o = linear_op(pzS.hi, pzS.lo, H, rw.d0z, rw.b_d0, 1, d1S.hi, d1S.lo, H);
+    o.addend = dh; o.ldadd = H;
+    const int op_d1 = pb.add_op(o);
+    o = linear_op(pzS.hi, pzS.lo, H, rw.ihz_p, rw.b_ih_p, 0, nullptr, nullptr, 0);
+    o.out_f = giz; o.ldo = 3 * H;
+    const int op_giz = pb.add_op(o);
+    const int op_d2 = pb.add_op(linear_op(d1S.hi, d1S.lo, H, rw.d2, w.b_d2, 1, d2S.hi, d2S.lo, H));
+    const int op_d3 = pb.add_op(linear_op(d2S.hi, d2S.lo, H, rw.d4, w.b_d4, 1, d3S.hi, d3S.lo, H));
+    o = linear_op(d3S.hi, d3S.lo, H, rw.d6, w.b_d6, 0, mnS.hi, mnS.lo, 128);
+    o.kind = rec::KIND_MEL;
+    const int op_mel = pb.add_op(o);
+    const int op_x1 = pb.add_op(linear_op(mnS.hi, mnS.lo, 128, rw.px0p, w.b_px0, 1, x1S.hi, x1S.lo, H));
+    const int op_x2 = pb.add_op(linear_op(x1S.hi, x1S.lo, H, rw.px2, w.b_px2, 1, x2S.hi, x2S.lo, H));
+    const int op_px = pb.add_op(linear_op(x2S.hi, x2S.lo, H, rw.px4, w.b_px4, 1, pxS.hi, pxS.lo, H));
+    o = linear_op(pxS.hi, pxS.lo, H, rw.ihx_p, nullptr, 0, hS.hi, hS.lo, H);
+    o.kind = rec::KIND_GRU; o.ni = 3;
+    o.addend = giz; o.ldadd = 3 * H;
+    const int op_gru = pb.add_op(o);
+
+    pb.crit = {{op_e1}, {op_e2}, {op_e4}, {op_z1}, {op_z2}, {op_pz}, {op_d1}, {op_d2}, {op_d3},
+               {op_mel}, {op_x1}, {op_x2}, {op_px}, {op_gru}};
+    pb.bg.push_back({op_dh, 0, 5, pb.tiles_of(p->ops[op_dh]), 0});
+    pb.bg.push_back({op_giz, 6, 12, pb.tiles_of(p->ops[op_giz]), 0});
+    pb.bg.push_back({op_gh, 0, 12, pb.tiles_of(p->ops[op_gh]), 0});
+    BVC_TRY(run_program(w, pb, s));
+    if (h_final) BVC_CUDA(cudaMemcpyAsync(h_final, hf, sizeof(float) * BH, cudaMemcpyDeviceToDevice, s));
+    return BVC_OK;
+}
+
+static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T,
+                                   float* mel, float* h_final, cudaStream_t s) {
+    const int H = w.H, X = w.X, Z = w.Z;
+    const size_t BT = (size_t)B * T;
+    RecurrentWeights& rw = w.rw;
+    int dev = 0, G = 0;
+    BVC_CUDA(cudaGetDevice(&dev));
+    BVC_TRY(rec::max_grid(dev, &G));
+    if (G > rec::MAX_GRID) G = rec::MAX_GRID;
+
+    float* PA = ws.take(BT * H);
+    float* PB = ws.take(BT * H);
+    float* DZ = ws.take(BT * 4 * H);
+    float* hf = ws.take((size_t)B * H);
+    float* gh = ws.take((size_t)B * 3 * H);
+    const size_t BH = (size_t)B * H;
+    SplitBuf hS = take_split(ws, BH), d1S = take_split(ws, BH), d2S = take_split(ws, BH), d3S = take_split(ws, BH);
+    SplitBuf mnS = take_split(ws, (size_t)B * 128), x1S = take_split(ws, BH), x2S = take_split(ws, BH);
+    SplitBuf pxS = take_split(ws, BH);
+
+    // hoisted over all frames: phi_z(z), then [dec.0_z ; W_ih_z (gate-interleaved)] . phi_z + [b_d0 ; b_ih]
+    BVC_TRY(run_linear(codes, Z, (int)BT, w.pz0, w.b_pz0, H, PA, H, 1, s));
+    BVC_TRY(run_linear(PA, H, (int)BT, w.pz2, w.b_pz2, H, PB, H, 1, s));
+    BVC_TRY(run_linear(PB, H, (int)BT, w.pz4, w.b_pz4, H, PA, H, 1, s));
+    BVC_TRY(run_linear(PA, H, (int)BT, rw.zcat_p, rw.b_zcat_p, 0, DZ, 4 * H, 1, s));
+    BVC_TRY(rec::init_state(h0, hf, hS.hi, hS.lo, (int)BH, mnS.hi, mnS.lo, B * 128, s));
+
+    rec::Program* p = rw.prog_host;
+    memset(p, 0, sizeof(rec::Program));
+    rec::Frame& fr = p->frame;
+    fr.M = B; fr.T = T; fr.X = X; fr.Z = Z; fr.H = H; fr.var_bit = w.var_bit;
+    fr.h = hf; fr.gh = gh; fr.mean = w.mean; fr.std = w.std; fr.mel_out = mel;
+
+    ProgramBuilder pb;
+    pb.p = p; pb.G = G; pb.M = B;
+    rec::Op o;
+    o = linear_op(hS.hi, hS.lo, H, rw.d0h, nullptr, 1, d1S.hi, d1S.lo, H);
+    o.addend = DZ; o.ldadd = T * 4 * H; o.add_tstride = 4 * H;       // includes dec.0 bias
+    const int op_d1 = pb.add_op(o);
+    o = linear_op(hS.hi, hS.lo, H, rw.whh_p, rw.b_hh_p, 0, nullptr, nullptr, 0);
+    o.out_f = gh; o.ldo = 3 * H;
+    const int op_gh = pb.add_op(o);
+    const int op_d2 = pb.add_op(linear_op(d1S.hi, d1S.lo, H, rw.d2, w.b_d2, 1, d2S.hi, d2S.lo, H));
+    const int op_d3 = pb.add_op(linear_op(d2S.hi, d2S.lo, H, rw.d4, w.b_d4, 1, d3S.hi, d3S.lo, H));
+    o = linear_op(d3S.hi, d3S.lo, H, rw.d6, w.b_d6, 0, mnS.hi, mnS.lo, 128);
+    o.kind = rec::KIND_MEL;
+    const int op_mel = pb.add_op(o);
+    const int op_x1 = pb.add_op(linear_op(mnS.hi, mnS.lo, 128, rw.px0p, w.b_px0, 1, x1S.hi, x1S.lo, H));
+    const int op_x2 = pb.add_op(linear_op(x1S.hi, x1S.lo, H, rw.px2, w.b_px2, 1, x2S.hi, x2S.lo, H));
+    const int op_px = pb.add_op(linear_op(x2S.hi, x2S.lo, H, rw.px4, w.b_px4, 1, pxS.hi, pxS.lo, H));
+    o = linear_op(pxS.hi, pxS.lo, H, rw.ihx_p, nullptr, 0, hS.hi, hS.lo, H);
+    o.kind = rec::KIND_GRU; o.ni = 3;
+    o.addend = DZ + H; o.ldadd = T * 4 * H; o.add_tstride = 4 * H;    // W_ih_z phi_z + b_ih, gate-interleaved
+    const int op_gru = pb.add_op(o);
+
+    pb.crit = {{op_d1}, {op_d2}, {op_d3}, {op_mel}, {op_x1}, {op_x2}, {op_px}, {op_gru}};
+    pb.bg.push_back({op_gh, 0, 6, pb.tiles_of(p->ops[op_gh]), 0});
+    BVC_TRY(run_program(w, pb, s));
+    if (h_final) BVC_CUDA(cudaMemcpyAsync(h_final, hf, sizeof(float) * BH, cudaMemcpyDeviceToDevice, s));
+    return BVC_OK;
+}
+
+int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
+                 const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
+                 float* all_h, float* h_final, int precision, cudaStream_t s) {
+    if (precision == 1 && w.rw.ready && w.Z == 64 && w.X <= 128)
+        return bvrnn_encode_persistent(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final, s);
+    return bvrnn_encode_layers(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final,
+                               precision, s);
+}
+
+int bvrnn_decode(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T, float* mel,
+                 float* h_final, int precision, cudaStream_t s) {
+    if (precision == 1 && w.rw.ready && w.Z == 64 && w.X <= 128)
+        return bvrnn_decode_persistent(w, ws, codes, h0, B, T, mel, h_final, s);
+    return bvrnn_decode_layers(w, ws, codes, h0, B, T, mel, h_final, precision, s);
 }
 
 }  // namespace bvc

@@ -1,6 +1,7 @@
 // Shared declarations for libbvc (sm_100a only).
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -81,6 +82,24 @@ int logmel_forward(const FrontendTables& ft, const float* x, int B, int L, int h
 // ---------------------------------------------------------------------------
 // BVRNN coder (bvrnn.cu)
 // ---------------------------------------------------------------------------
+// split-bf16 weight matrix [N][K] (nn.Linear layout), K % 64 == 0, for the persistent recurrent kernel
+struct SplitW {
+    const __nv_bfloat16* hi = nullptr;
+    const __nv_bfloat16* lo = nullptr;
+    int N = 0, K = 0;
+};
+namespace rec { struct Program; }
+struct RecurrentWeights {
+    bool ready = false;
+    SplitW e0h, d0h, whh_p, e2, e4, pz0, pz2, pz4, d0z, ihz_p, d2, d4, d6, px0p, px2, px4, ihx_p;
+    float *b_e0 = nullptr, *b_hh_p = nullptr, *b_d0 = nullptr, *b_ih_p = nullptr;
+    LinearWeights zcat_p;            // [dec.0[:, :H]; W_ih[:, H:] gate-interleaved] for the hoisted decode GEMM
+    float* b_zcat_p = nullptr;
+    unsigned* sync_words = nullptr;  // device: barrier counter, abort flag
+    rec::Program* prog_dev = nullptr;
+    rec::Program* prog_host = nullptr;   // pinned staging copy
+};
+
 struct BvrnnWeights {
     int X = 0, H = 0, Z = 0, var_bit = 0;
     float *mean = nullptr, *std = nullptr;
@@ -94,7 +113,8 @@ struct BvrnnWeights {
     LinearWeights zcat;               // [dec.0[:,:H]; W_ih[:,H:]]          N = 4H   (input phi_z)
     LinearWeights ihx;                // W_ih[:, :H]                        N = 3H   (input phi_x_gen)
     float *b_px0, *b_px2, *b_px4, *b_pz0, *b_pz2, *b_pz4, *b_e2, *b_e4, *b_d2, *b_d4, *b_d6;
-    float *b_hcat_enc, *b_hcat_dec, *b_zcat, *b_zcat_nod0;
+    float *b_hcat_enc, *b_hcat_dec, *b_zcat;
+    RecurrentWeights rw;
 };
 
 struct Workspace {
@@ -109,10 +129,10 @@ struct Workspace {
 };
 
 size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T);
-int bvrnn_encode(const BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
+int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
                  float* all_h, float* h_final, int precision, cudaStream_t stream);
-int bvrnn_decode(const BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T,
+int bvrnn_decode(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T,
                  float* mel, float* h_final, int precision, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
