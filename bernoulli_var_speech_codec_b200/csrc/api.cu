@@ -130,13 +130,13 @@ SplitW alias_split(const LinearWeights& lw) {
     s.K = lw.K;
     return s;
 }
-// GRU gate interleave: natural row gate*H + j  ->  24 (j / 8) + 8 gate + (j % 8), so that a 24-column
-// group holds r, z, n of 8 hidden units (recurrent.cu, KIND_GRU epilogue)
-std::vector<float> gate_interleave_rows(const std::vector<float>& w, int H, int K) {
+// GRU gate interleave: natural row gate*H + j  ->  3 grp (j / grp) + grp gate + (j % grp), so that a group of
+// 3 grp columns holds r, z, n of grp hidden units (recurrent_umma.cu, KIND_GRU epilogue; grp = 16)
+std::vector<float> gate_interleave_rows(const std::vector<float>& w, int H, int K, int grp) {
     std::vector<float> out(w.size());
     for (int gate = 0; gate < 3; ++gate)
         for (int j = 0; j < H; ++j)
-            memcpy(&out[(size_t)(24 * (j / 8) + 8 * gate + (j % 8)) * K], &w[(size_t)(gate * H + j) * K],
+            memcpy(&out[(size_t)(3 * grp * (j / grp) + grp * gate + (j % grp)) * K], &w[(size_t)(gate * H + j) * K],
                    sizeof(float) * K);
     return out;
 }
@@ -436,10 +436,6 @@ int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
         ok = ok && make_split(h, slice(e0, 0, H, H, 2 * H), Hi, Hi, Hi, &rw.e0h);
         ok = ok && make_split(h, slice(d0, 0, H, H, 2 * H), Hi, Hi, Hi, &rw.d0h);
         ok = ok && make_split(h, slice(d0, 0, H, 0, H), Hi, Hi, Hi, &rw.d0z);
-        ok = ok && make_split(h, gate_interleave_rows(to_vec(whh), Hi, Hi), 3 * Hi, Hi, Hi, &rw.whh_p);
-        const std::vector<float> ihz_p = gate_interleave_rows(slice(wih, 0, 3 * H, H, 2 * H), Hi, Hi);
-        ok = ok && make_split(h, ihz_p, 3 * Hi, Hi, Hi, &rw.ihz_p);
-        ok = ok && make_split(h, gate_interleave_rows(slice(wih, 0, 3 * H, 0, H), Hi, Hi), 3 * Hi, Hi, Hi, &rw.ihx_p);
         ok = ok && make_split(h, to_vec(m["phi_x.0.weight"]), Hi, Xi, ((Xi + 63) / 64) * 64, &rw.px0p);
         rw.e2 = alias_split(w.e2); rw.e4 = alias_split(w.e4);
         rw.pz0 = alias_split(w.pz0); rw.pz2 = alias_split(w.pz2); rw.pz4 = alias_split(w.pz4);
@@ -447,15 +443,21 @@ int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
         rw.px2 = alias_split(w.px2); rw.px4 = alias_split(w.px4);
         rw.b_e0 = up(to_vec(m["enc.0.bias"]));
         rw.b_d0 = up(to_vec(m["dec.0.bias"]));
-        const std::vector<float> bih_p = gate_interleave_rows(to_vec(m["rnn.bias_ih_l0"]), Hi, 1);
-        rw.b_hh_p = up(gate_interleave_rows(to_vec(m["rnn.bias_hh_l0"]), Hi, 1));
-        rw.b_ih_p = up(bih_p);
-        std::vector<float> zc = slice(d0, 0, H, 0, H);
-        append(zc, ihz_p);
-        ok = ok && make_linear(h, zc, 4 * Hi, Hi, &rw.zcat_p);
-        std::vector<float> bz = to_vec(m["dec.0.bias"]);
-        append(bz, bih_p);
-        rw.b_zcat_p = up(bz);
+        {   // GRU rows gate-interleaved in groups of 48
+            ok = ok && make_split(h, gate_interleave_rows(to_vec(whh), Hi, Hi, 16), 3 * Hi, Hi, Hi, &rw.whh_q);
+            const std::vector<float> ihz_q = gate_interleave_rows(slice(wih, 0, 3 * H, H, 2 * H), Hi, Hi, 16);
+            ok = ok && make_split(h, ihz_q, 3 * Hi, Hi, Hi, &rw.ihz_q);
+            ok = ok && make_split(h, gate_interleave_rows(slice(wih, 0, 3 * H, 0, H), Hi, Hi, 16), 3 * Hi, Hi, Hi, &rw.ihx_q);
+            const std::vector<float> bih_q = gate_interleave_rows(to_vec(m["rnn.bias_ih_l0"]), Hi, 1, 16);
+            rw.b_hh_q = up(gate_interleave_rows(to_vec(m["rnn.bias_hh_l0"]), Hi, 1, 16));
+            rw.b_ih_q = up(bih_q);
+            std::vector<float> zq = slice(d0, 0, H, 0, H);
+            append(zq, ihz_q);
+            ok = ok && make_linear(h, zq, 4 * Hi, Hi, &rw.zcat_q);
+            std::vector<float> bq = to_vec(m["dec.0.bias"]);
+            append(bq, bih_q);
+            rw.b_zcat_q = up(bq);
+        }
         void* p1 = nullptr; void* p2 = nullptr; void* p3 = nullptr;
         ok = ok && cudaMalloc(&p1, 16) == cudaSuccess && cudaMalloc(&p2, sizeof(rec::Program)) == cudaSuccess &&
              cudaMallocHost(&p3, sizeof(rec::Program)) == cudaSuccess;

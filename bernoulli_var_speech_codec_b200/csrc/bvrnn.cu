@@ -10,6 +10,7 @@
 // ([enc.0_h; dec.0_h; W_hh] . h), and the layers that read phi_z likewise
 // ([dec.0_z; W_ih_z] . phi_z), so a frame is 13 (encode) / 8 (decode) dependent GEMMs
 // plus the Bernoulli bottleneck and the GRU gate kernel.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -274,10 +275,11 @@ struct ProgramBuilder {
     std::vector<BgWork> bg;
 
     int tiles_of(const rec::Op& op) const {
-        const int bn = 32 * op.ni;
-        return ((M + 31) / 32) * ((op.N + bn - 1) / bn);
+        return ((M + 63) / 64) * ((op.N + op.bn - 1) / op.bn);
     }
-    double cost_of(const rec::Op& op) const { return (double)op.K * (32 + 32 * op.ni) / (1024.0 * 96.0); }
+    double cost_of(const rec::Op& op) const {
+        return (double)op.K * (64 + op.bn) / (1024.0 * 96.0);
+    }
 
     int add_op(const rec::Op& op) {
         p->ops[p->n_ops] = op;
@@ -346,7 +348,7 @@ rec::Op linear_op(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int lda,
     o.w_hi = w.hi; o.w_lo = w.lo; o.N = w.N; o.K = w.K;
     o.bias = bias; o.act = act;
     o.out_hi = out_hi; o.out_lo = out_lo; o.ldos = ldos;
-    o.ni = 2;
+    o.bn = 32;
     o.kind = rec::KIND_LINEAR;
     return o;
 }
@@ -362,20 +364,22 @@ SplitBuf take_split(Workspace& ws, size_t n) {
 }
 
 int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
+    if (const char* e = getenv("BVC_REC_DEBUG")) pb.p->debug_flags = atoi(e);
     if (!pb.schedule()) {
         set_error("recurrent program does not fit the static limits (MAX_TILES)");
         return BVC_ERR_INVALID;
     }
     // the pinned staging copy is reused by the next call: wait until the previous upload has been consumed
     BVC_CUDA(cudaMemcpyAsync(w.rw.prog_dev, w.rw.prog_host, sizeof(rec::Program), cudaMemcpyHostToDevice, s));
-    int rc = rec::launch(w.rw.prog_dev, pb.G, w.rw.sync_words, s);
+    int rc = rec::umma_launch(w.rw.prog_dev, pb.G, w.rw.sync_words, s);
     if (rc) return rc;
     // prog_host is overwritten by the next call; the copy above must have been issued from a stable buffer
     BVC_CUDA(cudaStreamSynchronize(s));
     unsigned flags[2];
     BVC_CUDA(cudaMemcpy(flags, w.rw.sync_words, sizeof(flags), cudaMemcpyDeviceToHost));
     if (flags[1] != 0) {
-        set_error("recurrent kernel aborted: device-wide barrier timed out");
+        set_error(flags[1] == 2 ? "recurrent kernel aborted: tensor-core pipeline (mbarrier) timed out"
+                                : "recurrent kernel aborted: device-wide barrier timed out");
         return BVC_ERR_DEVICE;
     }
     return BVC_OK;
@@ -438,7 +442,7 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     o = linear_op(hS.hi, hS.lo, H, rw.d0h, nullptr, 0, nullptr, nullptr, 0);
     o.out_f = dh; o.ldo = H;
     const int op_dh = pb.add_op(o);
-    o = linear_op(hS.hi, hS.lo, H, rw.whh_p, rw.b_hh_p, 0, nullptr, nullptr, 0);
+    o = linear_op(hS.hi, hS.lo, H, rw.whh_q, rw.b_hh_q, 0, nullptr, nullptr, 0);
     o.out_f = gh; o.ldo = 3 * H;
     const int op_gh = pb.add_op(o);
     const int op_e2 = pb.add_op(linear_op(e1S.hi, e1S.lo, H, rw.e2, w.b_e2, 1, e2S.hi, e2S.lo, H));
@@ -451,7 +455,7 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     o = linear_op(pzS.hi, pzS.lo, H, rw.d0z, rw.b_d0, 1, d1S.hi, d1S.lo, H);
     o.addend = dh; o.ldadd = H;
     const int op_d1 = pb.add_op(o);
-    o = linear_op(pzS.hi, pzS.lo, H, rw.ihz_p, rw.b_ih_p, 0, nullptr, nullptr, 0);
+    o = linear_op(pzS.hi, pzS.lo, H, rw.ihz_q, rw.b_ih_q, 0, nullptr, nullptr, 0);
     o.out_f = giz; o.ldo = 3 * H;
     const int op_giz = pb.add_op(o);
     const int op_d2 = pb.add_op(linear_op(d1S.hi, d1S.lo, H, rw.d2, w.b_d2, 1, d2S.hi, d2S.lo, H));
@@ -462,8 +466,8 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     const int op_x1 = pb.add_op(linear_op(mnS.hi, mnS.lo, 128, rw.px0p, w.b_px0, 1, x1S.hi, x1S.lo, H));
     const int op_x2 = pb.add_op(linear_op(x1S.hi, x1S.lo, H, rw.px2, w.b_px2, 1, x2S.hi, x2S.lo, H));
     const int op_px = pb.add_op(linear_op(x2S.hi, x2S.lo, H, rw.px4, w.b_px4, 1, pxS.hi, pxS.lo, H));
-    o = linear_op(pxS.hi, pxS.lo, H, rw.ihx_p, nullptr, 0, hS.hi, hS.lo, H);
-    o.kind = rec::KIND_GRU; o.ni = 3;
+    o = linear_op(pxS.hi, pxS.lo, H, rw.ihx_q, nullptr, 0, hS.hi, hS.lo, H);
+    o.kind = rec::KIND_GRU; o.bn = 48;
     o.addend = giz; o.ldadd = 3 * H;
     const int op_gru = pb.add_op(o);
 
@@ -501,7 +505,7 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     BVC_TRY(run_linear(codes, Z, (int)BT, w.pz0, w.b_pz0, H, PA, H, 1, s));
     BVC_TRY(run_linear(PA, H, (int)BT, w.pz2, w.b_pz2, H, PB, H, 1, s));
     BVC_TRY(run_linear(PB, H, (int)BT, w.pz4, w.b_pz4, H, PA, H, 1, s));
-    BVC_TRY(run_linear(PA, H, (int)BT, rw.zcat_p, rw.b_zcat_p, 0, DZ, 4 * H, 1, s));
+    BVC_TRY(run_linear(PA, H, (int)BT, rw.zcat_q, rw.b_zcat_q, 0, DZ, 4 * H, 1, s));
     BVC_TRY(rec::init_state(h0, hf, hS.hi, hS.lo, (int)BH, mnS.hi, mnS.lo, B * 128, s));
 
     rec::Program* p = rw.prog_host;
@@ -516,7 +520,7 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     o = linear_op(hS.hi, hS.lo, H, rw.d0h, nullptr, 1, d1S.hi, d1S.lo, H);
     o.addend = DZ; o.ldadd = T * 4 * H; o.add_tstride = 4 * H;       // includes dec.0 bias
     const int op_d1 = pb.add_op(o);
-    o = linear_op(hS.hi, hS.lo, H, rw.whh_p, rw.b_hh_p, 0, nullptr, nullptr, 0);
+    o = linear_op(hS.hi, hS.lo, H, rw.whh_q, rw.b_hh_q, 0, nullptr, nullptr, 0);
     o.out_f = gh; o.ldo = 3 * H;
     const int op_gh = pb.add_op(o);
     const int op_d2 = pb.add_op(linear_op(d1S.hi, d1S.lo, H, rw.d2, w.b_d2, 1, d2S.hi, d2S.lo, H));
@@ -527,8 +531,8 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     const int op_x1 = pb.add_op(linear_op(mnS.hi, mnS.lo, 128, rw.px0p, w.b_px0, 1, x1S.hi, x1S.lo, H));
     const int op_x2 = pb.add_op(linear_op(x1S.hi, x1S.lo, H, rw.px2, w.b_px2, 1, x2S.hi, x2S.lo, H));
     const int op_px = pb.add_op(linear_op(x2S.hi, x2S.lo, H, rw.px4, w.b_px4, 1, pxS.hi, pxS.lo, H));
-    o = linear_op(pxS.hi, pxS.lo, H, rw.ihx_p, nullptr, 0, hS.hi, hS.lo, H);
-    o.kind = rec::KIND_GRU; o.ni = 3;
+    o = linear_op(pxS.hi, pxS.lo, H, rw.ihx_q, nullptr, 0, hS.hi, hS.lo, H);
+    o.kind = rec::KIND_GRU; o.bn = 48;
     o.addend = DZ + H; o.ldadd = T * 4 * H; o.add_tstride = 4 * H;    // W_ih_z phi_z + b_ih, gate-interleaved
     const int op_gru = pb.add_op(o);
 
@@ -542,7 +546,7 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
 int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
                  float* all_h, float* h_final, int precision, cudaStream_t s) {
-    if (precision == 1 && w.rw.ready && w.Z == 64 && w.X <= 128)
+    if (precision >= 1 && w.rw.ready && w.Z == 64 && w.X <= 128)
         return bvrnn_encode_persistent(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final, s);
     return bvrnn_encode_layers(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final,
                                precision, s);
@@ -550,7 +554,7 @@ int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* 
 
 int bvrnn_decode(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T, float* mel,
                  float* h_final, int precision, cudaStream_t s) {
-    if (precision == 1 && w.rw.ready && w.Z == 64 && w.X <= 128)
+    if (precision >= 1 && w.rw.ready && w.Z == 64 && w.X <= 128)
         return bvrnn_decode_persistent(w, ws, codes, h0, B, T, mel, h_final, s);
     return bvrnn_decode_layers(w, ws, codes, h0, B, T, mel, h_final, precision, s);
 }

@@ -91,10 +91,11 @@ struct SplitW {
 namespace rec { struct Program; }
 struct RecurrentWeights {
     bool ready = false;
-    SplitW e0h, d0h, whh_p, e2, e4, pz0, pz2, pz4, d0z, ihz_p, d2, d4, d6, px0p, px2, px4, ihx_p;
-    float *b_e0 = nullptr, *b_hh_p = nullptr, *b_d0 = nullptr, *b_ih_p = nullptr;
-    LinearWeights zcat_p;            // [dec.0[:, :H]; W_ih[:, H:] gate-interleaved] for the hoisted decode GEMM
-    float* b_zcat_p = nullptr;
+    // *_q: GRU rows gate-interleaved in groups of 48 = [r(16) z(16) n(16)] (KIND_GRU epilogue)
+    SplitW e0h, d0h, whh_q, e2, e4, pz0, pz2, pz4, d0z, ihz_q, d2, d4, d6, px0p, px2, px4, ihx_q;
+    float *b_e0 = nullptr, *b_hh_q = nullptr, *b_d0 = nullptr, *b_ih_q = nullptr;
+    LinearWeights zcat_q;            // [dec.0[:, :H]; W_ih[:, H:] gate-interleaved] for the hoisted decode GEMM
+    float* b_zcat_q = nullptr;
     unsigned* sync_words = nullptr;  // device: barrier counter, abort flag
     rec::Program* prog_dev = nullptr;
     rec::Program* prog_host = nullptr;   // pinned staging copy

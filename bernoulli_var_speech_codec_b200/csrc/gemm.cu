@@ -284,7 +284,7 @@ int linear_forward(const float* A, int lda, int M, const LinearWeights& W, const
         return BVC_ERR_INVALID;
     }
     const int N = W.N, K = W.K;
-    if (precision == 1 && W.w_hi && (K % kTK) == 0) {
+    if (precision >= 1 && W.w_hi && (K % kTK) == 0) {
         if (M > 512) {
             constexpr int smem = (4 * 128 + 4 * 128) * kTPitch * 4;
             static bool attr_set = false;

@@ -1,4 +1,4 @@
-// Program format of the persistent recurrent kernel (recurrent.cu) and its host-side builder (bvrnn.cu).
+// Program format of the persistent recurrent kernel (recurrent_umma.cu) and its host-side builder (bvrnn.cu).
 #pragma once
 
 #include <cuda_bf16.h>
@@ -15,7 +15,7 @@ constexpr int MAX_PHASES = 16;
 constexpr int MAX_GRID = 160;
 constexpr int MAX_TILES = 6144;
 
-// One Linear layer evaluated as 32-row x (32 ni)-column tiles:  out = epilogue(A . W^T)
+// One Linear layer evaluated as 64-row x bn-column tiles:  out = epilogue(A . W^T)
 struct Op {
     const __nv_bfloat16* a_hi;     // activations, split bf16, [M][lda]
     const __nv_bfloat16* a_lo;     // may be null (exactly representable inputs)
@@ -30,9 +30,9 @@ struct Op {
     long long add_tstride;
     int lda, ldadd, ldo, ldos;
     int N, K;
-    int ni;                        // n8-tiles per warp: 2 (64-column tiles) or 3 (96-column, GRU)
     int kind;
     int act;                       // ELU
+    int bn;                        // tile width: 32, or 48 for the GRU layer
     int pad_;
 };
 
@@ -60,18 +60,18 @@ struct Program {
     int n_phases;
     int n_ops;
     int grid;
-    int pad_;
+    int debug_flags;               // experiments only: 1 skip copies, 2 skip MMAs, 4 skip epilogue, 8 skip grid barrier
     Op ops[MAX_OPS];
     int list_start[MAX_PHASES * MAX_GRID + 1];
     uint32_t tiles[MAX_TILES];
 };
 
-size_t smem_bytes();
 int max_grid(int device, int* out);
 int init_state(const float* h0, float* h, __nv_bfloat16* h_hi, __nv_bfloat16* h_lo, int n, __nv_bfloat16* mn_hi,
                __nv_bfloat16* mn_lo, int n_mn, cudaStream_t stream);
-int launch(const Program* prog_dev, int grid, unsigned* sync_words /* [0] barrier counter, [1] abort flag */,
-           cudaStream_t stream);
+size_t umma_smem_bytes();
+int umma_launch(const Program* prog_dev, int grid, unsigned* sync_words /* [0] barrier counter, [1] abort flag */,
+                cudaStream_t stream);
 
 }  // namespace rec
 }  // namespace bvc

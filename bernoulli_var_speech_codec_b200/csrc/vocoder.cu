@@ -506,7 +506,7 @@ template <int C, int U, int K>
 int launch_stage(const StageArgs& a, int B, int precision, cudaStream_t stream) {
     constexpr int HALO = 12 * (K - 1);
     dim3 grid((a.n_out + a.TT - 1) / a.TT, B);
-    if (precision == 1) {
+    if (precision >= 1) {
         const int W = a.TT + HALO;
         const size_t smem = (size_t)W * (RowLayout<C>::PF * 4 + 4 * RowLayout<C>::PW * 4);
         static bool attr_set = false;
