@@ -1,0 +1,25 @@
+"""Runs the vocoder on synthetic mel (for ncu captures of the stage kernels)."""
+import argparse, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bernoulli_var_speech_codec_b200 import BVRNNCodecModel, SCALING
+from bernoulli_var_speech_codec_b200.synth import write_synthetic_checkpoints
+ap = argparse.ArgumentParser()
+ap.add_argument("--precision", type=int, default=1)
+ap.add_argument("--B", type=int, default=64)
+ap.add_argument("--T", type=int, default=172)
+ap.add_argument("--reps", type=int, default=2)
+a = ap.parse_args()
+ck = write_synthetic_checkpoints(os.environ.get("BVC_CKPT_DIR", "/tmp/bvc_ckpts"), seed=1, sharpen=30.0)
+m = BVRNNCodecModel(os.path.join(ROOT, "configs", "config_varBitRate.toml"), *ck).eval()
+m._engine.set_precision(a.precision)
+g = torch.Generator().manual_seed(1)
+mel = (-5.0 + 2.0 * torch.randn(a.B, a.T, 80, generator=g)).cuda()
+for _ in range(a.reps):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    wav = m._engine.vocode(mel, a.T * 256, SCALING)
+    e1.record()
+torch.cuda.synchronize()
+print("ok", tuple(wav.shape), "vocode %.2f ms" % e0.elapsed_time(e1))
