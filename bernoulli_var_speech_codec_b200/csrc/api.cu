@@ -106,32 +106,42 @@ bool make_linear(bvc_handle* h, const std::vector<float>& w, int N, int K, Linea
     return true;
 }
 
-// split-bf16 copy [N][Kpad] (zero padded along K) for the persistent recurrent kernel
-bool make_split(bvc_handle* h, const std::vector<float>& w, int N, int K, int Kpad, SplitW* out) {
-    std::vector<uint16_t> hi((size_t)N * Kpad, 0), lo((size_t)N * Kpad, 0);
-    for (int n = 0; n < N; ++n)
-        for (int k = 0; k < K; ++k) {
-            const float v = w[(size_t)n * K + k];
-            const uint16_t vh = f2bf(v);
-            hi[(size_t)n * Kpad + k] = vh;
-            lo[(size_t)n * Kpad + k] = f2bf(v - bf2f(vh));
+// Split-bf16 shared-memory images of W [N][K] for the persistent recurrent kernel (layout: recurrent.cuh).
+// N is zero padded to a multiple of bn, K to a multiple of 64.
+bool make_wimg(bvc_handle* h, const std::vector<float>& w, int N, int K, int bn, WImg* out) {
+    const int n_tiles = (N + bn - 1) / bn, kch = (K + 63) / 64;
+    const size_t chunk = (size_t)2 * bn * 128;
+    std::vector<unsigned char> img((size_t)n_tiles * kch * chunk, 0);
+    for (int nt = 0; nt < n_tiles; ++nt)
+        for (int kc = 0; kc < kch; ++kc) {
+            unsigned char* base = img.data() + ((size_t)nt * kch + kc) * chunk;
+            for (int r = 0; r < bn; ++r) {
+                const int n = nt * bn + r;
+                if (n >= N) continue;
+                for (int kk = 0; kk < 64; ++kk) {
+                    const int k = kc * 64 + kk;
+                    if (k >= K) continue;
+                    const float v = w[(size_t)n * K + k];
+                    const uint16_t vh = f2bf(v), vl = f2bf(v - bf2f(vh));
+                    const size_t off = (size_t)r * 128 + ((((size_t)kk >> 3) ^ (size_t)(r & 7)) << 4) + (kk & 7) * 2;
+                    memcpy(base + off, &vh, 2);
+                    memcpy(base + (size_t)bn * 128 + off, &vl, 2);
+                }
+            }
         }
-    out->hi = reinterpret_cast<const __nv_bfloat16*>(dev_upload(h, hi));
-    out->lo = reinterpret_cast<const __nv_bfloat16*>(dev_upload(h, lo));
+    out->img = dev_upload(h, img);
     out->N = N;
-    out->K = Kpad;
-    return out->hi && out->lo;
+    out->K = K;
+    out->bn = bn;
+    return out->img != nullptr;
 }
-SplitW alias_split(const LinearWeights& lw) {
-    SplitW s;
-    s.hi = reinterpret_cast<const __nv_bfloat16*>(lw.w_hi);
-    s.lo = reinterpret_cast<const __nv_bfloat16*>(lw.w_lo);
-    s.N = lw.N;
-    s.K = lw.K;
-    return s;
+std::vector<float> pad_to(const std::vector<float>& v, size_t n) {
+    std::vector<float> o(v);
+    o.resize(n, 0.f);
+    return o;
 }
 // GRU gate interleave: natural row gate*H + j  ->  3 grp (j / grp) + grp gate + (j % grp), so that a group of
-// 3 grp columns holds r, z, n of grp hidden units (recurrent_umma.cu, KIND_GRU epilogue; grp = 16)
+// 3 grp columns holds r, z, n of grp hidden units (recurrent_cluster.cu, KIND_GRU epilogue; grp = 4)
 std::vector<float> gate_interleave_rows(const std::vector<float>& w, int H, int K, int grp) {
     std::vector<float> out(w.size());
     for (int gate = 0; gate < 3; ++gate)
@@ -432,24 +442,55 @@ int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
     ok = ok && make_linear(h, slice(wih, 0, 3 * H, 0, H), (int)(3 * H), (int)H, &w.ihx);
     {   // persistent recurrent kernel operands
         RecurrentWeights& rw = w.rw;
-        const int Hi = (int)H, Xi = (int)X;
-        ok = ok && make_split(h, slice(e0, 0, H, H, 2 * H), Hi, Hi, Hi, &rw.e0h);
-        ok = ok && make_split(h, slice(d0, 0, H, H, 2 * H), Hi, Hi, Hi, &rw.d0h);
-        ok = ok && make_split(h, slice(d0, 0, H, 0, H), Hi, Hi, Hi, &rw.d0z);
-        ok = ok && make_split(h, to_vec(m["phi_x.0.weight"]), Hi, Xi, ((Xi + 63) / 64) * 64, &rw.px0p);
-        rw.e2 = alias_split(w.e2); rw.e4 = alias_split(w.e4);
-        rw.pz0 = alias_split(w.pz0); rw.pz2 = alias_split(w.pz2); rw.pz4 = alias_split(w.pz4);
-        rw.d2 = alias_split(w.d2); rw.d4 = alias_split(w.d4); rw.d6 = alias_split(w.d6);
-        rw.px2 = alias_split(w.px2); rw.px4 = alias_split(w.px4);
+        const int Hi = (int)H, Xi = (int)X, Zi = (int)Z, G = 4;
+        auto W = [&](const std::vector<float>& v, int N, int K, int bn, WImg* o) { ok = ok && make_wimg(h, v, N, K, bn, o); };
+        W(slice(e0, 0, H, H, 2 * H), Hi, Hi, 64, &rw.e0h);
+        W(slice(d0, 0, H, H, 2 * H), Hi, Hi, 64, &rw.d0h);
+        W(slice(d0, 0, H, 0, H), Hi, Hi, 64, &rw.d0z);
+        W(to_vec(m["enc.2.weight"]), Hi, Hi, 64, &rw.e2);
+        W(to_vec(m["enc.4.weight"]), Zi, Hi, 64, &rw.e4);
+        W(to_vec(m["phi_z.0.weight"]), Hi, Zi, 16, &rw.pz0);
+        W(to_vec(m["phi_z.2.weight"]), Hi, Hi, 64, &rw.pz2);
+        W(to_vec(m["phi_z.4.weight"]), Hi, Hi, 64, &rw.pz4);
+        W(to_vec(m["dec.2.weight"]), Hi, Hi, 64, &rw.d2);
+        W(to_vec(m["dec.4.weight"]), Hi, Hi, 64, &rw.d4);
+        W(to_vec(m["dec.6.weight"]), Xi, Hi, 64, &rw.d6);
+        W(to_vec(m["phi_x.2.weight"]), Hi, Hi, 64, &rw.px2);
+        W(to_vec(m["phi_x.4.weight"]), Hi, Hi, 64, &rw.px4);
         rw.b_e0 = up(to_vec(m["enc.0.bias"]));
         rw.b_d0 = up(to_vec(m["dec.0.bias"]));
-        {   // GRU rows gate-interleaved in groups of 48
-            ok = ok && make_split(h, gate_interleave_rows(to_vec(whh), Hi, Hi, 16), 3 * Hi, Hi, Hi, &rw.whh_q);
-            const std::vector<float> ihz_q = gate_interleave_rows(slice(wih, 0, 3 * H, H, 2 * H), Hi, Hi, 16);
-            ok = ok && make_split(h, ihz_q, 3 * Hi, Hi, Hi, &rw.ihz_q);
-            ok = ok && make_split(h, gate_interleave_rows(slice(wih, 0, 3 * H, 0, H), Hi, Hi, 16), 3 * Hi, Hi, Hi, &rw.ihx_q);
-            const std::vector<float> bih_q = gate_interleave_rows(to_vec(m["rnn.bias_ih_l0"]), Hi, 1, 16);
-            rw.b_hh_q = up(gate_interleave_rows(to_vec(m["rnn.bias_hh_l0"]), Hi, 1, 16));
+        rw.b_d6p = up(pad_to(to_vec(m["dec.6.bias"]), (size_t)((Xi + 63) / 64) * 64));
+        {   // x1f = phi_x.0 . diag(1/std) . dec.6 ; bias = phi_x.0 . ((b_dec6 - mean) / std) + b_phi_x0   (float64)
+            const float* px0 = m["phi_x.0.weight"].data;      // [H, X]
+            const float* d6 = m["dec.6.weight"].data;          // [X, H]
+            const float* b6 = m["dec.6.bias"].data;
+            const float* bp = m["phi_x.0.bias"].data;
+            const float* mean = m["mean_mel"].data;
+            const float* sd = m["std_mel"].data;
+            std::vector<float> wf((size_t)H * H), bf((size_t)H);
+            std::vector<double> row((size_t)H);
+            for (int64_t i = 0; i < H; ++i) {
+                std::fill(row.begin(), row.end(), 0.0);
+                double bacc = bp[i];
+                for (int64_t j = 0; j < X; ++j) {
+                    const double c = (double)px0[i * X + j] / (double)sd[j];
+                    bacc += c * ((double)b6[j] - (double)mean[j]);
+                    const float* d6r = d6 + j * H;
+                    for (int64_t k = 0; k < H; ++k) row[k] += c * (double)d6r[k];
+                }
+                for (int64_t k = 0; k < H; ++k) wf[(size_t)i * H + k] = (float)row[k];
+                bf[i] = (float)bacc;
+            }
+            W(wf, Hi, Hi, 64, &rw.x1f);
+            rw.b_x1f = up(bf);
+        }
+        {   // GRU rows gate-interleaved in groups of 12 = [r(4) z(4) n(4)]
+            W(gate_interleave_rows(to_vec(whh), Hi, Hi, G), 3 * Hi, Hi, 64, &rw.whh_q);
+            const std::vector<float> ihz_q = gate_interleave_rows(slice(wih, 0, 3 * H, H, 2 * H), Hi, Hi, G);
+            W(ihz_q, 3 * Hi, Hi, 64, &rw.ihz_q);
+            W(gate_interleave_rows(slice(wih, 0, 3 * H, 0, H), Hi, Hi, G), 3 * Hi, Hi, 48, &rw.ihx_q);
+            const std::vector<float> bih_q = gate_interleave_rows(to_vec(m["rnn.bias_ih_l0"]), Hi, 1, G);
+            rw.b_hh_q = up(gate_interleave_rows(to_vec(m["rnn.bias_hh_l0"]), Hi, 1, G));
             rw.b_ih_q = up(bih_q);
             std::vector<float> zq = slice(d0, 0, H, 0, H);
             append(zq, ihz_q);
@@ -459,14 +500,14 @@ int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
             rw.b_zcat_q = up(bq);
         }
         void* p1 = nullptr; void* p2 = nullptr; void* p3 = nullptr;
-        ok = ok && cudaMalloc(&p1, 16) == cudaSuccess && cudaMalloc(&p2, sizeof(rec::Program)) == cudaSuccess &&
-             cudaMallocHost(&p3, sizeof(rec::Program)) == cudaSuccess;
+        ok = ok && cudaMalloc(&p1, rec::SYNC_WORDS * sizeof(unsigned)) == cudaSuccess &&
+             cudaMalloc(&p2, sizeof(rec::Program)) == cudaSuccess && cudaMallocHost(&p3, sizeof(rec::Program)) == cudaSuccess;
         if (p1) h->allocs.push_back(p1);
         if (p2) h->allocs.push_back(p2);
         rw.sync_words = (unsigned*)p1;
         rw.prog_dev = (rec::Program*)p2;
         rw.prog_host = (rec::Program*)p3;
-        rw.ready = ok && (H % 64 == 0) && (Z % 64 == 0) && X <= 128;
+        rw.ready = ok && (H % 256 == 0) && Z == 64 && X <= 128;
     }
     REQUIRE(ok, BVC_ERR_NOMEM, "device allocation failed while loading BVRNN weights");
     h->have_bvrnn = true;
@@ -796,7 +837,11 @@ int bvc_debug_read(bvc_handle* h, const char* name, float* dst_host, size_t n_fl
             avail = (size_t)vb.B * vb.C[i + 1] * vb.n[i + 1];
         }
     }
-    REQUIRE(src && vb.B > 0, BVC_ERR_INVALID, "bvc_debug_read: unknown buffer or no vocoder call yet: " + nm);
+    const RecurrentWeights& rw = h->bw.rw;
+    if (nm == "rec_dh") { src = rw.tap_dh; avail = (size_t)rw.tap_B * h->bw.H; }
+    if (nm == "rec_gh") { src = rw.tap_gh; avail = (size_t)rw.tap_B * 3 * h->bw.H; }
+    if (nm == "rec_giz") { src = rw.tap_giz; avail = (size_t)rw.tap_B * 3 * h->bw.H; }
+    REQUIRE(src && avail > 0, BVC_ERR_INVALID, "bvc_debug_read: unknown buffer or no call has filled it yet: " + nm);
     REQUIRE(n_floats <= avail, BVC_ERR_INVALID, "bvc_debug_read: buffer holds fewer floats than requested");
     BVC_CUDA(cudaDeviceSynchronize());
     BVC_CUDA(cudaMemcpy(dst_host, src, n_floats * sizeof(float), cudaMemcpyDeviceToHost));

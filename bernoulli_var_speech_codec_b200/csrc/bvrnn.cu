@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -106,11 +107,12 @@ int run_linear(const float* A, int lda, int M, const LinearWeights& w, const flo
 
 size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T) {
     const size_t BT = (size_t)B * T, H = w.H;
+    const size_t Bp = ((size_t)B + 127) / 128 * 128;   // activation images cover whole 128-row m-tiles
     size_t n = 0;
     n += BT * w.X + 64;                 // normalised mel
     n += 2 * (BT * H + 64);             // two hoisted activation buffers
     n += BT * 4 * H + 64;               // decode: hoisted [dec.0_z ; W_ih_z] . phi_z
-    n += (size_t)B * (40 * H + 2 * w.X + 2 * w.Z + 256) + 64 * 64;
+    n += Bp * (40 * H + 2 * w.X + 2 * w.Z + 256) + 64 * 64;
     return n;
 }
 
@@ -260,132 +262,126 @@ static int bvrnn_decode_layers(BvrnnWeights& w, Workspace& ws, const float* code
 
 
 // =============================================================================================
-// Persistent-kernel path (precision 1): host-side program builder and scheduler
+// Persistent-kernel path (precision 1): host-side program builder
 // =============================================================================================
 namespace {
 
-struct BgWork {
-    int op, first_phase, last_phase, n_tiles, next_tile;
+struct PhaseSpec {
+    const unsigned char* a_img;
+    int k_chunks;
+    int split;
+    std::vector<int> ops;
 };
 
 struct ProgramBuilder {
     rec::Program* p;
-    int G, M;
-    std::vector<std::vector<int>> crit;   // per phase: critical op indices
-    std::vector<BgWork> bg;
-
-    int tiles_of(const rec::Op& op) const {
-        return ((M + 63) / 64) * ((op.N + op.bn - 1) / op.bn);
-    }
-    double cost_of(const rec::Op& op) const {
-        return (double)op.K * (64 + op.bn) / (1024.0 * 96.0);
-    }
+    int n_clusters, M;
+    std::vector<PhaseSpec> phases;
 
     int add_op(const rec::Op& op) {
         p->ops[p->n_ops] = op;
         return p->n_ops++;
     }
+    void add_phase(const unsigned char* a_img, int K, int split, std::vector<int> ops) {
+        phases.push_back({a_img, K / rec::CHUNK_K, split, std::move(ops)});
+    }
 
-    // Greedy list scheduler: critical tiles round-robin over the CTAs; background tiles fill the slack of a
-    // phase (earliest deadline first) and whatever is left at an op's deadline is spread over the least-loaded CTAs.
-    bool schedule() {
-        const int n_ph = (int)crit.size();
-        p->n_phases = n_ph;
-        p->grid = G;
-        int n_list = 0;
-        std::vector<std::vector<uint32_t>> lists(G);
-        std::vector<double> load(G);
-        const double full = 1.0;
-        for (int ph = 0; ph < n_ph; ++ph) {
-            for (auto& l : lists) l.clear();
-            std::fill(load.begin(), load.end(), 0.0);
-            int rr = 0;
-            for (int oi : crit[ph]) {
-                const int nt = tiles_of(p->ops[oi]);
-                const double c = cost_of(p->ops[oi]);
-                for (int t = 0; t < nt; ++t) {
-                    lists[rr].push_back(((uint32_t)oi << 20) | (uint32_t)t);
-                    load[rr] += c;
-                    rr = (rr + 1) % G;
-                }
-            }
-            double lmax = *std::max_element(load.begin(), load.end());
-            if (lmax < full) lmax = full;
-            std::vector<BgWork*> ready;
-            for (auto& b : bg)
-                if (b.first_phase <= ph && ph <= b.last_phase && b.next_tile < b.n_tiles) ready.push_back(&b);
-            std::sort(ready.begin(), ready.end(), [](BgWork* a, BgWork* b) { return a->last_phase < b->last_phase; });
-            for (BgWork* b : ready) {
-                const double c = cost_of(p->ops[b->op]);
-                const bool deadline = (b->last_phase == ph);
-                while (b->next_tile < b->n_tiles) {
-                    const int cta = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-                    if (!deadline && load[cta] + c > lmax + 1e-9) break;
-                    lists[cta].push_back(((uint32_t)b->op << 20) | (uint32_t)b->next_tile++);
-                    load[cta] += c;
-                }
-            }
-            for (int c = 0; c < G; ++c) {
-                p->list_start[ph * G + c] = n_list;
-                for (uint32_t e : lists[c]) {
-                    if (n_list >= rec::MAX_TILES) return false;
-                    p->tiles[n_list++] = e;
-                }
-            }
+    // Clusters are dealt to m-tiles in contiguous, equal blocks (an m-tile is a barrier domain); the n-tiles
+    // of a phase's ops are dealt round-robin to the clusters of each m-tile.
+    bool finish() {
+        const int n_mt = (M + rec::TILE_M - 1) / rec::TILE_M;
+        if (n_mt > n_clusters || n_mt > rec::MAX_MTILES || (int)phases.size() > rec::MAX_PHASES) return false;
+        p->n_clusters = n_clusters;
+        p->n_mtiles = n_mt;
+        p->n_phases = (int)phases.size();
+        std::vector<std::vector<int>> of_mtile(n_mt);
+        for (int c = 0; c < n_clusters; ++c) {
+            const int mt = (int)((long long)c * n_mt / n_clusters);
+            p->cluster_mtile[c] = mt;
+            of_mtile[mt].push_back(c);
         }
-        p->list_start[n_ph * G] = n_list;
-        for (auto& b : bg)
-            if (b.next_tile < b.n_tiles) return false;
+        for (int mt = 0; mt < n_mt; ++mt) p->mtile_ctas[mt] = rec::CLUSTER * (int)of_mtile[mt].size();
+        int n_e = 0;
+        for (int ph = 0; ph < p->n_phases; ++ph) {
+            p->phases[ph].a_img = phases[ph].a_img;
+            p->phases[ph].k_chunks = phases[ph].k_chunks;
+            p->phases[ph].split = phases[ph].split;
+            std::vector<std::vector<uint32_t>> lists(n_clusters);
+            for (int mt = 0; mt < n_mt; ++mt) {
+                int rr = 0;
+                const std::vector<int>& cl = of_mtile[mt];
+                for (int oi : phases[ph].ops) {
+                    const rec::Op& op = p->ops[oi];
+                    const int n_tiles = (op.N + op.bn - 1) / op.bn;
+                    for (int nt = 0; nt < n_tiles; ++nt) {
+                        lists[cl[rr]].push_back(((uint32_t)oi << 16) | (uint32_t)nt);
+                        rr = (rr + 1) % (int)cl.size();
+                    }
+                }
+            }
+            for (int c = 0; c < n_clusters; ++c) {
+                p->entry_start[ph * (n_clusters + 1) + c] = n_e;
+                for (uint32_t e : lists[c]) {
+                    if (n_e >= rec::MAX_ENTRIES) return false;
+                    p->entries[n_e++] = e;
+                }
+            }
+            p->entry_start[ph * (n_clusters + 1) + n_clusters] = n_e;
+        }
         return true;
     }
 };
 
-rec::Op linear_op(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int lda, const SplitW& w, const float* bias,
-                  int act, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldos) {
+rec::Op linear_op(const WImg& w, const float* bias, int act, unsigned char* out_img, int out_kchunks) {
     rec::Op o;
     memset(&o, 0, sizeof(o));
-    o.a_hi = a_hi; o.a_lo = a_lo; o.lda = lda;
-    o.w_hi = w.hi; o.w_lo = w.lo; o.N = w.N; o.K = w.K;
+    o.w_img = w.img; o.N = w.N; o.bn = w.bn;
     o.bias = bias; o.act = act;
-    o.out_hi = out_hi; o.out_lo = out_lo; o.ldos = ldos;
-    o.bn = 32;
+    o.out_img = out_img; o.out_kchunks = out_kchunks;
     o.kind = rec::KIND_LINEAR;
     return o;
 }
 
-struct SplitBuf {
-    __nv_bfloat16 *hi, *lo;
-};
-SplitBuf take_split(Workspace& ws, size_t n) {
-    SplitBuf b;
-    b.hi = reinterpret_cast<__nv_bfloat16*>(ws.take((n + 1) / 2));
-    b.lo = reinterpret_cast<__nv_bfloat16*>(ws.take((n + 1) / 2));
-    return b;
+// activation images for an [m_tiles * 128, K] matrix
+unsigned char* take_img(Workspace& ws, int M, int K) {
+    const size_t bytes = (size_t)((M + rec::TILE_M - 1) / rec::TILE_M) * (K / rec::CHUNK_K) * rec::ACT_CHUNK_BYTES;
+    return reinterpret_cast<unsigned char*>(ws.take(bytes / sizeof(float)));
 }
 
 int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
     if (const char* e = getenv("BVC_REC_DEBUG")) pb.p->debug_flags = atoi(e);
-    if (!pb.schedule()) {
-        set_error("recurrent program does not fit the static limits (MAX_TILES)");
+    if (!pb.finish()) {
+        set_error("recurrent program does not fit the static limits (m-tiles / entries)");
         return BVC_ERR_INVALID;
     }
-    // the pinned staging copy is reused by the next call: wait until the previous upload has been consumed
     BVC_CUDA(cudaMemcpyAsync(w.rw.prog_dev, w.rw.prog_host, sizeof(rec::Program), cudaMemcpyHostToDevice, s));
-    int rc = rec::umma_launch(w.rw.prog_dev, pb.G, w.rw.sync_words, s);
+    int rc = rec::launch(w.rw.prog_dev, pb.n_clusters, w.rw.sync_words, s);
     if (rc) return rc;
-    // prog_host is overwritten by the next call; the copy above must have been issued from a stable buffer
+    // prog_host is overwritten by the next call, and a failed kernel must be reported by this one
     BVC_CUDA(cudaStreamSynchronize(s));
-    unsigned flags[2];
-    BVC_CUDA(cudaMemcpy(flags, w.rw.sync_words, sizeof(flags), cudaMemcpyDeviceToHost));
-    if (flags[1] != 0) {
-        set_error(flags[1] == 2 ? "recurrent kernel aborted: tensor-core pipeline (mbarrier) timed out"
-                                : "recurrent kernel aborted: device-wide barrier timed out");
+    int flag = 0;
+    BVC_CUDA(cudaMemcpy(&flag, w.rw.sync_words, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag != 0) {
+        set_error("recurrent kernel aborted: " +
+                  std::string(flag == 1 ? "phase barrier timed out" : "pipeline wait timed out, code " + std::to_string(flag)));
         return BVC_ERR_DEVICE;
     }
     return BVC_OK;
 }
 
+int cluster_count(int* out) {
+    int dev = 0;
+    BVC_CUDA(cudaGetDevice(&dev));
+    return rec::max_clusters(dev, out);
+}
+
 }  // namespace
+
+// rows per persistent-kernel call: every m-tile needs a cluster, and the entry table is finite
+static int persistent_max_rows(int n_clusters) {
+    const int mt = n_clusters < 16 ? n_clusters : 16;
+    return mt * rec::TILE_M;
+}
 
 static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits,
                                    float bits_scalar, const float* h0, int B, int T, float* codes,
@@ -394,10 +390,8 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     const int H = w.H, X = w.X, Z = w.Z;
     const size_t BT = (size_t)B * T;
     RecurrentWeights& rw = w.rw;
-    int dev = 0, G = 0;
-    BVC_CUDA(cudaGetDevice(&dev));
-    BVC_TRY(rec::max_grid(dev, &G));
-    if (G > rec::MAX_GRID) G = rec::MAX_GRID;
+    int G = 0;
+    BVC_TRY(cluster_count(&G));
 
     float* yn = ws.take(BT * X);
     float* PA = ws.take(BT * H);
@@ -406,12 +400,13 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     float* dh = ws.take((size_t)B * H);
     float* gh = ws.take((size_t)B * 3 * H);
     float* giz = ws.take((size_t)B * 3 * H);
-    const size_t BH = (size_t)B * H;
-    SplitBuf hS = take_split(ws, BH), e1S = take_split(ws, BH), e2S = take_split(ws, BH);
-    SplitBuf zS = take_split(ws, (size_t)B * Z), z1S = take_split(ws, BH), z2S = take_split(ws, BH);
-    SplitBuf pzS = take_split(ws, BH), d1S = take_split(ws, BH), d2S = take_split(ws, BH), d3S = take_split(ws, BH);
-    SplitBuf mnS = take_split(ws, (size_t)B * 128), x1S = take_split(ws, BH), x2S = take_split(ws, BH);
-    SplitBuf pxS = take_split(ws, BH);
+    rw.tap_dh = dh; rw.tap_gh = gh; rw.tap_giz = giz; rw.tap_B = B;
+    const int KH = H / rec::CHUNK_K;
+    unsigned char *hI = take_img(ws, B, H), *e1I = take_img(ws, B, H), *e2I = take_img(ws, B, H);
+    unsigned char *zI = take_img(ws, B, Z), *z1I = take_img(ws, B, H), *z2I = take_img(ws, B, H);
+    unsigned char *pzI = take_img(ws, B, H), *d1I = take_img(ws, B, H), *d2I = take_img(ws, B, H);
+    unsigned char *d3I = take_img(ws, B, H), *x1I = take_img(ws, B, H), *x2I = take_img(ws, B, H);
+    unsigned char* pxI = take_img(ws, B, H);
 
     // hoisted over all frames (large GEMMs): phi_x(yn), then enc.0[:, :H] . phi_x
     {
@@ -424,60 +419,68 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     BVC_TRY(run_linear(PB, H, (int)BT, w.px4, w.b_px4, H, PA, H, 1, s));
     BVC_TRY(run_linear(PA, H, (int)BT, w.e0x, nullptr, 0, PB, H, 1, s));
     float* E0x = PB;
-    BVC_TRY(rec::init_state(h0, hf, hS.hi, hS.lo, (int)BH, mnS.hi, mnS.lo, B * 128, s));
+    BVC_TRY(rec::init_state(h0, hf, hI, B, H, s));
 
     rec::Program* p = rw.prog_host;
     memset(p, 0, sizeof(rec::Program));
     rec::Frame& fr = p->frame;
     fr.M = B; fr.T = T; fr.X = X; fr.Z = Z; fr.H = H; fr.var_bit = w.var_bit;
     fr.bits_scalar = bits_scalar; fr.bits = bits; fr.codes = codes; fr.packed = packed; fr.logits = logits;
-    fr.all_h = all_h; fr.h = hf; fr.gh = gh; fr.mean = w.mean; fr.std = w.std; fr.mel_out = nullptr;
+    fr.all_h = all_h; fr.h = hf; fr.h_img = hI; fr.gh = gh; fr.mel_out = nullptr;
 
     ProgramBuilder pb;
-    pb.p = p; pb.G = G; pb.M = B;
+    pb.p = p; pb.n_clusters = G; pb.M = B;
     rec::Op o;
-    o = linear_op(hS.hi, hS.lo, H, rw.e0h, rw.b_e0, 1, e1S.hi, e1S.lo, H);
+    // layers that read h: enc.0_h (critical), dec.0_h and W_hh (consumed later in the frame)
+    o = linear_op(rw.e0h, rw.b_e0, 1, e1I, KH);
     o.addend = E0x; o.ldadd = T * H; o.add_tstride = H;
     const int op_e1 = pb.add_op(o);
-    o = linear_op(hS.hi, hS.lo, H, rw.d0h, nullptr, 0, nullptr, nullptr, 0);
+    o = linear_op(rw.d0h, nullptr, 0, nullptr, 0);
     o.out_f = dh; o.ldo = H;
     const int op_dh = pb.add_op(o);
-    o = linear_op(hS.hi, hS.lo, H, rw.whh_q, rw.b_hh_q, 0, nullptr, nullptr, 0);
+    o = linear_op(rw.whh_q, rw.b_hh_q, 0, nullptr, 0);
     o.out_f = gh; o.ldo = 3 * H;
     const int op_gh = pb.add_op(o);
-    const int op_e2 = pb.add_op(linear_op(e1S.hi, e1S.lo, H, rw.e2, w.b_e2, 1, e2S.hi, e2S.lo, H));
-    o = linear_op(e2S.hi, e2S.lo, H, rw.e4, w.b_e4, 0, zS.hi, zS.lo, Z);
+    const int op_e2 = pb.add_op(linear_op(rw.e2, w.b_e2, 1, e2I, KH));
+    o = linear_op(rw.e4, w.b_e4, 0, zI, Z / rec::CHUNK_K);
     o.kind = rec::KIND_BOTTLENECK;
     const int op_e4 = pb.add_op(o);
-    const int op_z1 = pb.add_op(linear_op(zS.hi, nullptr, Z, rw.pz0, w.b_pz0, 1, z1S.hi, z1S.lo, H));
-    const int op_z2 = pb.add_op(linear_op(z1S.hi, z1S.lo, H, rw.pz2, w.b_pz2, 1, z2S.hi, z2S.lo, H));
-    const int op_pz = pb.add_op(linear_op(z2S.hi, z2S.lo, H, rw.pz4, w.b_pz4, 1, pzS.hi, pzS.lo, H));
-    o = linear_op(pzS.hi, pzS.lo, H, rw.d0z, rw.b_d0, 1, d1S.hi, d1S.lo, H);
+    const int op_z1 = pb.add_op(linear_op(rw.pz0, w.b_pz0, 1, z1I, KH));
+    const int op_z2 = pb.add_op(linear_op(rw.pz2, w.b_pz2, 1, z2I, KH));
+    const int op_pz = pb.add_op(linear_op(rw.pz4, w.b_pz4, 1, pzI, KH));
+    // layers that read phi_z: dec.0_z (critical) and W_ih_z (consumed by the GRU)
+    o = linear_op(rw.d0z, rw.b_d0, 1, d1I, KH);
     o.addend = dh; o.ldadd = H;
     const int op_d1 = pb.add_op(o);
-    o = linear_op(pzS.hi, pzS.lo, H, rw.ihz_q, rw.b_ih_q, 0, nullptr, nullptr, 0);
+    o = linear_op(rw.ihz_q, rw.b_ih_q, 0, nullptr, 0);
     o.out_f = giz; o.ldo = 3 * H;
     const int op_giz = pb.add_op(o);
-    const int op_d2 = pb.add_op(linear_op(d1S.hi, d1S.lo, H, rw.d2, w.b_d2, 1, d2S.hi, d2S.lo, H));
-    const int op_d3 = pb.add_op(linear_op(d2S.hi, d2S.lo, H, rw.d4, w.b_d4, 1, d3S.hi, d3S.lo, H));
-    o = linear_op(d3S.hi, d3S.lo, H, rw.d6, w.b_d6, 0, mnS.hi, mnS.lo, 128);
-    o.kind = rec::KIND_MEL;
-    const int op_mel = pb.add_op(o);
-    const int op_x1 = pb.add_op(linear_op(mnS.hi, mnS.lo, 128, rw.px0p, w.b_px0, 1, x1S.hi, x1S.lo, H));
-    const int op_x2 = pb.add_op(linear_op(x1S.hi, x1S.lo, H, rw.px2, w.b_px2, 1, x2S.hi, x2S.lo, H));
-    const int op_px = pb.add_op(linear_op(x2S.hi, x2S.lo, H, rw.px4, w.b_px4, 1, pxS.hi, pxS.lo, H));
-    o = linear_op(pxS.hi, pxS.lo, H, rw.ihx_q, nullptr, 0, hS.hi, hS.lo, H);
-    o.kind = rec::KIND_GRU; o.bn = 48;
+    const int op_d2 = pb.add_op(linear_op(rw.d2, w.b_d2, 1, d2I, KH));
+    const int op_d3 = pb.add_op(linear_op(rw.d4, w.b_d4, 1, d3I, KH));
+    // phi_x.0 of the reconstruction, fused with dec.6 and the mel normalisation (bvrnn.py:202-204)
+    const int op_x1 = pb.add_op(linear_op(rw.x1f, rw.b_x1f, 1, x1I, KH));
+    const int op_x2 = pb.add_op(linear_op(rw.px2, w.b_px2, 1, x2I, KH));
+    const int op_px = pb.add_op(linear_op(rw.px4, w.b_px4, 1, pxI, KH));
+    o = linear_op(rw.ihx_q, nullptr, 0, hI, KH);
+    o.kind = rec::KIND_GRU;
     o.addend = giz; o.ldadd = 3 * H;
     const int op_gru = pb.add_op(o);
 
-    pb.crit = {{op_e1}, {op_e2}, {op_e4}, {op_z1}, {op_z2}, {op_pz}, {op_d1}, {op_d2}, {op_d3},
-               {op_mel}, {op_x1}, {op_x2}, {op_px}, {op_gru}};
-    pb.bg.push_back({op_dh, 0, 5, pb.tiles_of(p->ops[op_dh]), 0});
-    pb.bg.push_back({op_giz, 6, 12, pb.tiles_of(p->ops[op_giz]), 0});
-    pb.bg.push_back({op_gh, 0, 12, pb.tiles_of(p->ops[op_gh]), 0});
+    pb.add_phase(hI, H, 1, {op_e1, op_dh, op_gh});
+    pb.add_phase(e1I, H, 1, {op_e2});
+    pb.add_phase(e2I, H, 1, {op_e4});
+    pb.add_phase(zI, Z, 0, {op_z1});
+    pb.add_phase(z1I, H, 1, {op_z2});
+    pb.add_phase(z2I, H, 1, {op_pz});
+    pb.add_phase(pzI, H, 1, {op_d1, op_giz});
+    pb.add_phase(d1I, H, 1, {op_d2});
+    pb.add_phase(d2I, H, 1, {op_d3});
+    pb.add_phase(d3I, H, 1, {op_x1});
+    pb.add_phase(x1I, H, 1, {op_x2});
+    pb.add_phase(x2I, H, 1, {op_px});
+    pb.add_phase(pxI, H, 1, {op_gru});
     BVC_TRY(run_program(w, pb, s));
-    if (h_final) BVC_CUDA(cudaMemcpyAsync(h_final, hf, sizeof(float) * BH, cudaMemcpyDeviceToDevice, s));
+    if (h_final) BVC_CUDA(cudaMemcpyAsync(h_final, hf, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, s));
     return BVC_OK;
 }
 
@@ -486,77 +489,103 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     const int H = w.H, X = w.X, Z = w.Z;
     const size_t BT = (size_t)B * T;
     RecurrentWeights& rw = w.rw;
-    int dev = 0, G = 0;
-    BVC_CUDA(cudaGetDevice(&dev));
-    BVC_TRY(rec::max_grid(dev, &G));
-    if (G > rec::MAX_GRID) G = rec::MAX_GRID;
+    int G = 0;
+    BVC_TRY(cluster_count(&G));
 
     float* PA = ws.take(BT * H);
     float* PB = ws.take(BT * H);
     float* DZ = ws.take(BT * 4 * H);
     float* hf = ws.take((size_t)B * H);
     float* gh = ws.take((size_t)B * 3 * H);
-    const size_t BH = (size_t)B * H;
-    SplitBuf hS = take_split(ws, BH), d1S = take_split(ws, BH), d2S = take_split(ws, BH), d3S = take_split(ws, BH);
-    SplitBuf mnS = take_split(ws, (size_t)B * 128), x1S = take_split(ws, BH), x2S = take_split(ws, BH);
-    SplitBuf pxS = take_split(ws, BH);
+    const int KH = H / rec::CHUNK_K;
+    unsigned char *hI = take_img(ws, B, H), *d1I = take_img(ws, B, H), *d2I = take_img(ws, B, H);
+    unsigned char *d3I = take_img(ws, B, H), *x1I = take_img(ws, B, H), *x2I = take_img(ws, B, H);
+    unsigned char* pxI = take_img(ws, B, H);
 
     // hoisted over all frames: phi_z(z), then [dec.0_z ; W_ih_z (gate-interleaved)] . phi_z + [b_d0 ; b_ih]
     BVC_TRY(run_linear(codes, Z, (int)BT, w.pz0, w.b_pz0, H, PA, H, 1, s));
     BVC_TRY(run_linear(PA, H, (int)BT, w.pz2, w.b_pz2, H, PB, H, 1, s));
     BVC_TRY(run_linear(PB, H, (int)BT, w.pz4, w.b_pz4, H, PA, H, 1, s));
     BVC_TRY(run_linear(PA, H, (int)BT, rw.zcat_q, rw.b_zcat_q, 0, DZ, 4 * H, 1, s));
-    BVC_TRY(rec::init_state(h0, hf, hS.hi, hS.lo, (int)BH, mnS.hi, mnS.lo, B * 128, s));
+    BVC_TRY(rec::init_state(h0, hf, hI, B, H, s));
 
     rec::Program* p = rw.prog_host;
     memset(p, 0, sizeof(rec::Program));
     rec::Frame& fr = p->frame;
     fr.M = B; fr.T = T; fr.X = X; fr.Z = Z; fr.H = H; fr.var_bit = w.var_bit;
-    fr.h = hf; fr.gh = gh; fr.mean = w.mean; fr.std = w.std; fr.mel_out = mel;
+    fr.h = hf; fr.h_img = hI; fr.gh = gh; fr.mel_out = mel;
 
     ProgramBuilder pb;
-    pb.p = p; pb.G = G; pb.M = B;
+    pb.p = p; pb.n_clusters = G; pb.M = B;
     rec::Op o;
-    o = linear_op(hS.hi, hS.lo, H, rw.d0h, nullptr, 1, d1S.hi, d1S.lo, H);
+    o = linear_op(rw.d0h, nullptr, 1, d1I, KH);
     o.addend = DZ; o.ldadd = T * 4 * H; o.add_tstride = 4 * H;       // includes dec.0 bias
     const int op_d1 = pb.add_op(o);
-    o = linear_op(hS.hi, hS.lo, H, rw.whh_q, rw.b_hh_q, 0, nullptr, nullptr, 0);
+    o = linear_op(rw.whh_q, rw.b_hh_q, 0, nullptr, 0);
     o.out_f = gh; o.ldo = 3 * H;
     const int op_gh = pb.add_op(o);
-    const int op_d2 = pb.add_op(linear_op(d1S.hi, d1S.lo, H, rw.d2, w.b_d2, 1, d2S.hi, d2S.lo, H));
-    const int op_d3 = pb.add_op(linear_op(d2S.hi, d2S.lo, H, rw.d4, w.b_d4, 1, d3S.hi, d3S.lo, H));
-    o = linear_op(d3S.hi, d3S.lo, H, rw.d6, w.b_d6, 0, mnS.hi, mnS.lo, 128);
+    const int op_d2 = pb.add_op(linear_op(rw.d2, w.b_d2, 1, d2I, KH));
+    const int op_d3 = pb.add_op(linear_op(rw.d4, w.b_d4, 1, d3I, KH));
+    o = linear_op(rw.d6, rw.b_d6p, 0, nullptr, 0);                    // the decoder's output (bvrnn.py:225)
     o.kind = rec::KIND_MEL;
     const int op_mel = pb.add_op(o);
-    const int op_x1 = pb.add_op(linear_op(mnS.hi, mnS.lo, 128, rw.px0p, w.b_px0, 1, x1S.hi, x1S.lo, H));
-    const int op_x2 = pb.add_op(linear_op(x1S.hi, x1S.lo, H, rw.px2, w.b_px2, 1, x2S.hi, x2S.lo, H));
-    const int op_px = pb.add_op(linear_op(x2S.hi, x2S.lo, H, rw.px4, w.b_px4, 1, pxS.hi, pxS.lo, H));
-    o = linear_op(pxS.hi, pxS.lo, H, rw.ihx_q, nullptr, 0, hS.hi, hS.lo, H);
-    o.kind = rec::KIND_GRU; o.bn = 48;
+    const int op_x1 = pb.add_op(linear_op(rw.x1f, rw.b_x1f, 1, x1I, KH));
+    const int op_x2 = pb.add_op(linear_op(rw.px2, w.b_px2, 1, x2I, KH));
+    const int op_px = pb.add_op(linear_op(rw.px4, w.b_px4, 1, pxI, KH));
+    o = linear_op(rw.ihx_q, nullptr, 0, hI, KH);
+    o.kind = rec::KIND_GRU;
     o.addend = DZ + H; o.ldadd = T * 4 * H; o.add_tstride = 4 * H;    // W_ih_z phi_z + b_ih, gate-interleaved
     const int op_gru = pb.add_op(o);
 
-    pb.crit = {{op_d1}, {op_d2}, {op_d3}, {op_mel}, {op_x1}, {op_x2}, {op_px}, {op_gru}};
-    pb.bg.push_back({op_gh, 0, 6, pb.tiles_of(p->ops[op_gh]), 0});
+    pb.add_phase(hI, H, 1, {op_d1, op_gh});
+    pb.add_phase(d1I, H, 1, {op_d2});
+    pb.add_phase(d2I, H, 1, {op_d3});
+    pb.add_phase(d3I, H, 1, {op_x1, op_mel});
+    pb.add_phase(x1I, H, 1, {op_x2});
+    pb.add_phase(x2I, H, 1, {op_px});
+    pb.add_phase(pxI, H, 1, {op_gru});
     BVC_TRY(run_program(w, pb, s));
-    if (h_final) BVC_CUDA(cudaMemcpyAsync(h_final, hf, sizeof(float) * BH, cudaMemcpyDeviceToDevice, s));
+    if (h_final) BVC_CUDA(cudaMemcpyAsync(h_final, hf, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, s));
     return BVC_OK;
 }
 
 int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
                  float* all_h, float* h_final, int precision, cudaStream_t s) {
-    if (precision >= 1 && w.rw.ready && w.Z == 64 && w.X <= 128)
-        return bvrnn_encode_persistent(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final, s);
-    return bvrnn_encode_layers(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final,
-                               precision, s);
+    if (!(precision >= 1 && w.rw.ready))
+        return bvrnn_encode_layers(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final,
+                                   precision, s);
+    int G = 0;
+    BVC_TRY(cluster_count(&G));
+    const int max_rows = persistent_max_rows(G);
+    const size_t mark = ws.used, T_ = (size_t)T;
+    for (int b0 = 0; b0 < B; b0 += max_rows) {      // utterances are independent: chunk very large batches
+        const int nb = B - b0 < max_rows ? B - b0 : max_rows;
+        const size_t r = (size_t)b0;
+        ws.used = mark;
+        BVC_TRY(bvrnn_encode_persistent(w, ws, mel + r * T_ * w.X, bits ? bits + r * T_ : nullptr, bits_scalar,
+                                        h0 ? h0 + r * w.H : nullptr, nb, T, codes + r * T_ * w.Z,
+                                        packed ? packed + r * T_ : nullptr, logits ? logits + r * T_ * w.Z : nullptr,
+                                        all_h ? all_h + r * T_ * w.H : nullptr, h_final ? h_final + r * w.H : nullptr, s));
+    }
+    return BVC_OK;
 }
 
 int bvrnn_decode(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T, float* mel,
                  float* h_final, int precision, cudaStream_t s) {
-    if (precision >= 1 && w.rw.ready && w.Z == 64 && w.X <= 128)
-        return bvrnn_decode_persistent(w, ws, codes, h0, B, T, mel, h_final, s);
-    return bvrnn_decode_layers(w, ws, codes, h0, B, T, mel, h_final, precision, s);
+    if (!(precision >= 1 && w.rw.ready)) return bvrnn_decode_layers(w, ws, codes, h0, B, T, mel, h_final, precision, s);
+    int G = 0;
+    BVC_TRY(cluster_count(&G));
+    const int max_rows = persistent_max_rows(G);
+    const size_t mark = ws.used, T_ = (size_t)T;
+    for (int b0 = 0; b0 < B; b0 += max_rows) {
+        const int nb = B - b0 < max_rows ? B - b0 : max_rows;
+        const size_t r = (size_t)b0;
+        ws.used = mark;
+        BVC_TRY(bvrnn_decode_persistent(w, ws, codes + r * T_ * w.Z, h0 ? h0 + r * w.H : nullptr, nb, T,
+                                        mel + r * T_ * w.X, h_final ? h_final + r * w.H : nullptr, s));
+    }
+    return BVC_OK;
 }
 
 }  // namespace bvc

@@ -82,23 +82,30 @@ int logmel_forward(const FrontendTables& ft, const float* x, int B, int L, int h
 // ---------------------------------------------------------------------------
 // BVRNN coder (bvrnn.cu)
 // ---------------------------------------------------------------------------
-// split-bf16 weight matrix [N][K] (nn.Linear layout), K % 64 == 0, for the persistent recurrent kernel
-struct SplitW {
-    const __nv_bfloat16* hi = nullptr;
-    const __nv_bfloat16* lo = nullptr;
-    int N = 0, K = 0;
+// Weight matrix [N][K] (nn.Linear layout) as split-bf16 shared-memory images for the persistent recurrent
+// kernel: [n_tile][k_chunk] chunks of bn rows x 64 columns, hi part then lo part, SWIZZLE_128B (recurrent.cuh)
+struct WImg {
+    const unsigned char* img = nullptr;
+    int N = 0, K = 0, bn = 0;
 };
 namespace rec { struct Program; }
 struct RecurrentWeights {
     bool ready = false;
-    // *_q: GRU rows gate-interleaved in groups of 48 = [r(16) z(16) n(16)] (KIND_GRU epilogue)
-    SplitW e0h, d0h, whh_q, e2, e4, pz0, pz2, pz4, d0z, ihz_q, d2, d4, d6, px0p, px2, px4, ihx_q;
-    float *b_e0 = nullptr, *b_hh_q = nullptr, *b_d0 = nullptr, *b_ih_q = nullptr;
+    // *_q: GRU rows gate-interleaved in groups of 12 = [r(4) z(4) n(4)] (KIND_GRU epilogue: after the cluster's
+    // reduce-scatter a CTA owns 12 of the 48 columns of a tile, i.e. all three gates of 4 hidden units)
+    // x1f: phi_x.0 . diag(1/std) . dec.6 -- dec.6, the mel normalisation and phi_x.0 are all affine, so the
+    // reconstructed mel never has to exist on the recurrence's critical path (bvrnn.py:202-204)
+    WImg e0h, d0h, whh_q, e2, e4, pz0, pz2, pz4, d0z, ihz_q, d2, d4, d6, x1f, px2, px4, ihx_q;
+    float *b_e0 = nullptr, *b_hh_q = nullptr, *b_d0 = nullptr, *b_ih_q = nullptr, *b_x1f = nullptr, *b_d6p = nullptr;
     LinearWeights zcat_q;            // [dec.0[:, :H]; W_ih[:, H:] gate-interleaved] for the hoisted decode GEMM
     float* b_zcat_q = nullptr;
-    unsigned* sync_words = nullptr;  // device: barrier counter, abort flag
+    unsigned* sync_words = nullptr;  // device: abort flag + one barrier counter per m-tile
     rec::Program* prog_dev = nullptr;
     rec::Program* prog_host = nullptr;   // pinned staging copy
+    // parity taps of the last encode call (views into the workspace): dec.0_h . h [B,H], W_hh h + b [B,3H] and
+    // W_ih_z phi_z + b [B,3H] of the LAST frame, the latter two with gate-interleaved columns
+    const float *tap_dh = nullptr, *tap_gh = nullptr, *tap_giz = nullptr;
+    int tap_B = 0;
 };
 
 struct BvrnnWeights {

@@ -1,4 +1,13 @@
-// Program format of the persistent recurrent kernel (recurrent_umma.cu) and its host-side builder (bvrnn.cu).
+// Program format of the persistent recurrent kernel (recurrent_cluster.cu) and its host-side builder (bvrnn.cu).
+//
+// Operand "images".  Every matrix the kernel reads is stored in global memory as the exact shared-memory
+// image the tensor core wants, so that one bulk copy (cp.async.bulk, no tensor map) moves a whole operand
+// chunk and no thread ever computes a swizzled address while loading:
+//   chunk      = R rows x 64 bf16 (128 bytes per row), hi part followed by lo part (split bf16, x = hi + lo)
+//   row r      = 128 contiguous bytes at r * 128; its 16-byte piece c is stored at piece position c ^ (r & 7)
+//                (the UMMA canonical K-major SWIZZLE_128B layout, SBO = 1024 bytes)
+//   activation = [m_tile][k_chunk] chunks of R = 128 rows            (32 KiB each)
+//   weight     = [n_tile][k_chunk] chunks of R = bn rows (bn = 64, 48 or 16; nn.Linear row = output feature)
 #pragma once
 
 #include <cuda_bf16.h>
@@ -10,30 +19,41 @@ namespace rec {
 
 enum Kind { KIND_LINEAR = 0, KIND_BOTTLENECK = 1, KIND_MEL = 2, KIND_GRU = 3 };
 
+constexpr int CLUSTER = 4;          // CTAs per cluster = K split of a layer
+constexpr int TILE_M = 128;         // batch rows per m-tile (UMMA M)
+constexpr int CHUNK_K = 64;         // K elements per chunk
+constexpr int ACT_PART_BYTES = TILE_M * 128;
+constexpr int ACT_CHUNK_BYTES = 2 * ACT_PART_BYTES;
+
 constexpr int MAX_OPS = 24;
 constexpr int MAX_PHASES = 16;
-constexpr int MAX_GRID = 160;
-constexpr int MAX_TILES = 6144;
+constexpr int MAX_CLUSTERS = 32;
+constexpr int MAX_MTILES = 32;
+constexpr int MAX_ENTRIES = 8192;
 
-// One Linear layer evaluated as 64-row x bn-column tiles:  out = epilogue(A . W^T)
+// One Linear layer:  out = epilogue(A . W^T), evaluated as 128-row x bn-column tiles.
 struct Op {
-    const __nv_bfloat16* a_hi;     // activations, split bf16, [M][lda]
-    const __nv_bfloat16* a_lo;     // may be null (exactly representable inputs)
-    const __nv_bfloat16* w_hi;     // weights, split bf16, [N][K] (nn.Linear layout), K % 64 == 0
-    const __nv_bfloat16* w_lo;
-    const float* bias;             // [N] or null
+    const unsigned char* w_img;    // weight images [n_tiles][k_chunks], chunk = 2 * bn * 128 bytes
+    const float* bias;             // [n_tiles * bn] or null
     const float* addend;           // fp32 [M][ldadd] (+ t * add_tstride) or null
     float* out_f;                  // fp32 [M][ldo] or null
-    __nv_bfloat16* out_hi;         // split bf16 [M][ldos] or null
-    __nv_bfloat16* out_lo;
-    long long a_tstride;           // elements added to a_hi / a_lo per frame
+    unsigned char* out_img;        // activation images of the output [m_tiles][out_kchunks] or null
     long long add_tstride;
-    int lda, ldadd, ldo, ldos;
-    int N, K;
+    int ldadd, ldo;
+    int out_kchunks;
+    int N;                         // valid output columns
+    int bn;                        // tile width: 64 (split-K), 48 (GRU, split-K) or 16 (K = 64 layers, no split)
     int kind;
     int act;                       // ELU
-    int bn;                        // tile width: 32, or 48 for the GRU layer
     int pad_;
+};
+
+// All ops of a phase read the same activation matrix A.
+struct Phase {
+    const unsigned char* a_img;    // activation images [m_tiles][k_chunks]
+    int k_chunks;                  // K / 64
+    int split;                     // 1: the 4 CTAs of a cluster each take K/4 and reduce through DSMEM
+                                   // 0: each CTA takes every 4th entry of its cluster's list with the full K
 };
 
 // per-call constants shared by the epilogues
@@ -47,31 +67,37 @@ struct Frame {
     float* logits;                 // [M][T][Z] or null
     float* all_h;                  // [M][T][H] or null
     float* h;                      // [M][H] fp32 state (updated in place)
+    unsigned char* h_img;          // activation images of h
     const float* gh;               // [M][3H] W_hh h + b_hh, gate-interleaved columns
-    const float* mean;
-    const float* std;
     float* mel_out;                // [M][T][X] or null
 };
 
-// A frame = n_phases phases; phase p, CTA c executes tiles[list_start[p*G + c] .. list_start[p*G + c + 1]).
-// A tile entry is (op index << 20) | tile index.
+// A frame = n_phases phases.  Cluster c works on m-tile cluster_mtile[c]; in phase p it executes the entries
+// entries[entry_start[p * (n_clusters + 1) + c] .. entry_start[p * (n_clusters + 1) + c + 1]).
+// An entry is (op index << 16) | n-tile index.  Phases are separated by a barrier over the CTAs of one m-tile.
 struct Program {
     Frame frame;
     int n_phases;
     int n_ops;
-    int grid;
-    int debug_flags;               // experiments only: 1 skip copies, 2 skip MMAs, 4 skip epilogue, 8 skip grid barrier
+    int n_clusters;
+    int n_mtiles;
+    int debug_flags;
+    int pad_;
     Op ops[MAX_OPS];
-    int list_start[MAX_PHASES * MAX_GRID + 1];
-    uint32_t tiles[MAX_TILES];
+    Phase phases[MAX_PHASES];
+    int cluster_mtile[MAX_CLUSTERS];
+    int mtile_ctas[MAX_MTILES];    // CTAs per barrier domain
+    int entry_start[MAX_PHASES * (MAX_CLUSTERS + 1)];
+    uint32_t entries[MAX_ENTRIES];
 };
 
-int max_grid(int device, int* out);
-int init_state(const float* h0, float* h, __nv_bfloat16* h_hi, __nv_bfloat16* h_lo, int n, __nv_bfloat16* mn_hi,
-               __nv_bfloat16* mn_lo, int n_mn, cudaStream_t stream);
-size_t umma_smem_bytes();
-int umma_launch(const Program* prog_dev, int grid, unsigned* sync_words /* [0] barrier counter, [1] abort flag */,
-                cudaStream_t stream);
+int max_clusters(int device, int* out);
+size_t smem_bytes();
+// h0 (or zeros) -> fp32 state + activation images of the state
+int init_state(const float* h0, float* h, unsigned char* h_img, int M, int H, cudaStream_t stream);
+int launch(const Program* prog_dev, int n_clusters, unsigned* sync_words /* [0] abort flag, [32 (1 + m)] barrier of m-tile m */,
+           cudaStream_t stream);
+constexpr int SYNC_WORDS = 32 * (1 + MAX_MTILES);
 
 }  // namespace rec
 }  // namespace bvc
