@@ -10,6 +10,7 @@
 // ([enc.0_h; dec.0_h; W_hh] . h), and the layers that read phi_z likewise
 // ([dec.0_z; W_ih_z] . phi_z), so a frame is 13 (encode) / 8 (decode) dependent GEMMs
 // plus the Bernoulli bottleneck and the GRU gate kernel.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -354,11 +355,33 @@ int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
         set_error("recurrent program does not fit the static limits (m-tiles / entries)");
         return BVC_ERR_INVALID;
     }
+    // bring-up: BVC_REC_TRACE=<file> dumps per-CTA, per-phase %globaltimer stamps of the first frames
+    const char* trace_path = getenv("BVC_REC_TRACE");
+    const int trace_frames = 6, n_ctas = pb.n_clusters * rec::CLUSTER;
+    const size_t trace_n = (size_t)n_ctas * trace_frames * rec::MAX_PHASES * rec::TRACE_EVENTS;
+    unsigned long long* trace_dev = nullptr;
+    if (trace_path) {
+        BVC_CUDA(cudaMalloc(&trace_dev, trace_n * sizeof(unsigned long long)));
+        BVC_CUDA(cudaMemsetAsync(trace_dev, 0, trace_n * sizeof(unsigned long long), s));
+        pb.p->trace = trace_dev;
+        pb.p->trace_frames = trace_frames;
+    }
     BVC_CUDA(cudaMemcpyAsync(w.rw.prog_dev, w.rw.prog_host, sizeof(rec::Program), cudaMemcpyHostToDevice, s));
     int rc = rec::launch(w.rw.prog_dev, pb.n_clusters, w.rw.sync_words, s);
     if (rc) return rc;
     // prog_host is overwritten by the next call, and a failed kernel must be reported by this one
     BVC_CUDA(cudaStreamSynchronize(s));
+    if (trace_dev) {
+        std::vector<unsigned long long> hbuf(trace_n);
+        BVC_CUDA(cudaMemcpy(hbuf.data(), trace_dev, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(trace_dev);
+        if (FILE* f = fopen(trace_path, "wb")) {
+            const int hdr[4] = {n_ctas, trace_frames, rec::MAX_PHASES, rec::TRACE_EVENTS};
+            fwrite(hdr, sizeof(int), 4, f);
+            fwrite(hbuf.data(), sizeof(unsigned long long), trace_n, f);
+            fclose(f);
+        }
+    }
     int flag = 0;
     BVC_CUDA(cudaMemcpy(&flag, w.rw.sync_words, sizeof(flag), cudaMemcpyDeviceToHost));
     if (flag != 0) {
@@ -379,7 +402,10 @@ int cluster_count(int* out) {
 
 // rows per persistent-kernel call: every m-tile needs a cluster, and the entry table is finite
 static int persistent_max_rows(int n_clusters) {
-    const int mt = n_clusters < 16 ? n_clusters : 16;
+    // at least two clusters per m-tile keep a CTA's per-frame entry list within the kernel's shared-memory table
+    int mt = n_clusters / 2;
+    if (mt > 16) mt = 16;
+    if (mt < 1) mt = 1;
     return mt * rec::TILE_M;
 }
 

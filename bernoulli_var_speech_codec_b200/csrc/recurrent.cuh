@@ -25,7 +25,7 @@ constexpr int CHUNK_K = 64;         // K elements per chunk
 constexpr int ACT_PART_BYTES = TILE_M * 128;
 constexpr int ACT_CHUNK_BYTES = 2 * ACT_PART_BYTES;
 
-constexpr int MAX_OPS = 24;
+constexpr int MAX_OPS = 20;
 constexpr int MAX_PHASES = 16;
 constexpr int MAX_CLUSTERS = 32;
 constexpr int MAX_MTILES = 32;
@@ -82,7 +82,8 @@ struct Program {
     int n_clusters;
     int n_mtiles;
     int debug_flags;
-    int pad_;
+    int trace_frames;              // bring-up: per CTA, frame < trace_frames, phase: TRACE_EVENTS %globaltimer stamps
+    unsigned long long* trace;
     Op ops[MAX_OPS];
     Phase phases[MAX_PHASES];
     int cluster_mtile[MAX_CLUSTERS];
@@ -98,6 +99,7 @@ int init_state(const float* h0, float* h, unsigned char* h_img, int M, int H, cu
 int launch(const Program* prog_dev, int n_clusters, unsigned* sync_words /* [0] abort flag, [32 (1 + m)] barrier of m-tile m */,
            cudaStream_t stream);
 constexpr int SYNC_WORDS = 32 * (1 + MAX_MTILES);
+constexpr int TRACE_EVENTS = 16;
 
 }  // namespace rec
 }  // namespace bvc

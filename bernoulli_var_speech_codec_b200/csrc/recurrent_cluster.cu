@@ -50,7 +50,7 @@ constexpr int SMEM_A = 0;
 constexpr int SMEM_W = SMEM_A + A_SLOTS * ACT_CHUNK_BYTES;
 constexpr int SMEM_STG = SMEM_W + W_SLOTS * W_SLOT_BYTES;
 constexpr int SMEM_TOTAL = SMEM_STG + 2 * STG_BUF_BYTES;     // 224 KiB
-constexpr int SMEM_DYNAMIC = SMEM_TOTAL + 1024;              // manual 1024-byte alignment
+constexpr int SMEM_DYNAMIC = SMEM_TOTAL + 3072;              // control block (3 KiB) in front; the whole 227 KiB of the SM
 
 struct Bars {
     uint64_t fullA[A_SLOTS];       // activation chunk landed (expect_tx)
@@ -59,7 +59,7 @@ struct Bars {
     uint64_t accFull[ACC_SLOTS];   // accumulator complete (tcgen05.commit)
     uint64_t accEmpty[ACC_SLOTS];  // accumulator drained (4 epilogue warps)
     uint64_t aFree;                // all MMAs of the job retired: activation buffer reusable
-    uint64_t stgFull[2];           // the 3 peers wrote their partials into my staging buffer
+    uint64_t stgFull[2];           // the 3 peers' partials have landed in my staging buffer (expect_tx / st.async complete_tx)
     uint64_t stgEmpty[2];          // the 3 peers finished reading their staging buffer
 };
 
@@ -120,14 +120,19 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
     return r;
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+// "I have read my staging buffer": pure flow control, no data is published by it.  A release-scoped arrive costs a
+// full MEMBAR.ALL.GPU per call in SASS; the reads it follows have already returned their values (they were consumed
+// by the additions before it in program order), so the relaxed form is sufficient.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void st_cluster_f4(uint32_t cluster_addr, float a, float b, float c, float d) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d)
+// 16-byte store into a peer's shared memory that also counts 16 bytes on the peer's mbarrier: data and signal travel
+// together, so the sender needs no fence and no separate arrive
+__device__ __forceinline__ void st_async_f4(uint32_t cluster_addr, uint32_t cluster_mbar, float a, float b, float c, float d) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n" ::"r"(cluster_addr),
+                 "f"(a), "f"(b), "f"(c), "f"(d), "r"(cluster_mbar)
                  : "memory");
 }
-__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
@@ -201,21 +206,15 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     return v;
 }
 
-// The entries of (phase, cluster) this CTA executes: index e0 + i * stride, i < n.
-struct JobView {
-    int e0, n, stride;
-};
-__device__ __forceinline__ JobView my_entries(const Program* p, int ph, int cluster, int rank) {
-    const int* es = p->entry_start + ph * (p->n_clusters + 1) + cluster;
-    const int eb = es[0], cnt = es[1] - es[0];
-    JobView v;
-    if (p->phases[ph].split) {
-        v.e0 = eb; v.n = cnt; v.stride = 1;
-    } else {
-        v.e0 = eb + rank; v.n = cnt > rank ? (cnt - rank + CLUSTER - 1) / CLUSTER : 0; v.stride = CLUSTER;
-    }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(v));
     return v;
 }
+#define BVC_TRACE(ev)                                                                                             \
+    do {                                                                                                          \
+        if (trace && t < trace_frames) trace[(((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS + (ev)] = global_ns(); \
+    } while (0)
 
 // 16 consecutive values of activation row `row` (columns col0 .. col0+15, col0 % 16 == 0) -> image of the
 // consumer layer: two 16-byte pieces of the hi part and of the lo part
@@ -236,10 +235,18 @@ __device__ __forceinline__ void store_img16(unsigned char* img, int m_tile, int 
     *reinterpret_cast<uint4*>(base + ACT_PART_BYTES + p1) = l1;
 }
 
-__device__ __forceinline__ void load16(const float* p, float* v, bool through_l2) {
+// loads that may have been written by another CTA in an earlier phase go through L2 (ld.cg)
+__device__ __forceinline__ void load16_cg(const float* p, float* v) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float4 a = through_l2 ? __ldcg(reinterpret_cast<const float4*>(p) + i) : __ldg(reinterpret_cast<const float4*>(p) + i);
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(p) + i);
+        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+    }
+}
+__device__ __forceinline__ void load12_cg(const float* p, float* v) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(p) + i);
         v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
     }
 }
@@ -248,38 +255,58 @@ __device__ __forceinline__ void store16(float* p, const float* v) {
     for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
+// Operands of an epilogue that do not depend on the accumulator; fetched while the MMAs are still running.
+struct Prefetch {
+    float a[16];     // LINEAR: bias + addend.  GRU: W_ih_z phi_z + b_ih of the 12 columns
+    float b[16];     // GRU: [0..11] W_hh h + b_hh of the 12 columns, [12..15] the 4 states
+    float budget;    // BOTTLENECK: bit budget of (m, t)
+};
+
+__device__ __forceinline__ void prefetch_epilogue(const Op& op, const Frame& fr, int t, int m, int col0, int u0, Prefetch& pf) {
+    if (m >= fr.M) return;
+    if (op.kind == KIND_GRU) {
+        load12_cg(op.addend + (size_t)t * op.add_tstride + (size_t)m * op.ldadd + col0, pf.a);
+        load12_cg(fr.gh + (size_t)m * 3 * fr.H + col0, pf.b);
+        const float4 hv = *reinterpret_cast<const float4*>(fr.h + (size_t)m * fr.H + u0);   // only this thread touches them
+        pf.b[12] = hv.x; pf.b[13] = hv.y; pf.b[14] = hv.z; pf.b[15] = hv.w;
+        return;
+    }
+    if (op.bias) load16_cg(op.bias + col0, pf.a);
+    else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pf.a[i] = 0.f;
+    }
+    if (op.addend) {
+        float tmp[16];
+        load16_cg(op.addend + (size_t)t * op.add_tstride + (size_t)m * op.ldadd + col0, tmp);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pf.a[i] += tmp[i];
+    }
+    if (op.kind == KIND_BOTTLENECK) pf.budget = fr.bits ? __ldg(fr.bits + (size_t)m * fr.T + t) : fr.bits_scalar;
+}
+
 // Epilogue of 16 output columns (col0 .. col0+15) of row m.  v = A.W^T summed over the whole K.
 __device__ __forceinline__ void finalize16(const Op& op, const Frame& fr, int t, int m, int row, int m_tile, int col0,
-                                           float* v) {
+                                           float* v, const Prefetch& pf) {
     if (m >= fr.M) return;
-    float tmp[16];
-    if (op.bias) {
-        load16(op.bias + col0, tmp, false);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += tmp[i];
-    }
-    if (op.addend) {   // written by another CTA in an earlier phase or by an earlier kernel: read through L2
-        load16(op.addend + (size_t)t * op.add_tstride + (size_t)m * op.ldadd + col0, tmp, true);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += tmp[i];
-    }
+    for (int i = 0; i < 16; ++i) v[i] += pf.a[i];
     if (op.kind == KIND_BOTTLENECK) {
         // z = round(sigmoid(logit)), masked to 0.5 beyond the frame's bit budget (bvrnn.py:191-196)
-        const float budget = fr.bits ? __ldg(fr.bits + (size_t)m * fr.T + t) : fr.bits_scalar;
         float code[16];
         uint32_t word = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const bool active = !fr.var_bit || (budget > (float)(col0 + i));
+            const bool active = !fr.var_bit || (pf.budget > (float)(col0 + i));
             const bool bit = active && (sigmoidf_(v[i]) > 0.5f);
             code[i] = active ? (bit ? 1.f : 0.f) : 0.5f;
             if (bit) word |= 1u << i;
         }
+        store_img16(op.out_img, m_tile, op.out_kchunks, row, col0, code, true);   // {0, .5, 1} are exact in bf16
         const size_t o = ((size_t)m * fr.T + t) * fr.Z + col0;
         store16(fr.codes + o, code);
         if (fr.logits) store16(fr.logits + o, v);
         if (fr.packed) reinterpret_cast<unsigned short*>(fr.packed)[((size_t)m * fr.T + t) * 4 + (col0 >> 4)] = (unsigned short)word;
-        store_img16(op.out_img, m_tile, op.out_kchunks, row, col0, code, true);   // {0, .5, 1} are exact in bf16
         return;
     }
     if (op.act) {
@@ -296,38 +323,24 @@ __device__ __forceinline__ void finalize16(const Op& op, const Frame& fr, int t,
         }
         return;
     }
-    if (op.out_f && col0 < op.N) store16(op.out_f + (size_t)m * op.ldo + col0, v);
     if (op.out_img && col0 < op.N) store_img16(op.out_img, m_tile, op.out_kchunks, row, col0, v, false);
+    if (op.out_f && col0 < op.N) store16(op.out_f + (size_t)m * op.ldo + col0, v);
 }
 
 // GRU epilogue: 12 columns = [r(4) | z(4) | n(4)] of the hidden units u0 .. u0+3 (PyTorch gate order r,z,n;
 // reference bvrnn.py:83,206):  r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r * gh_n), h' = (h - n) z + n
-__device__ __forceinline__ void finalize_gru(const Op& op, const Frame& fr, int t, int m, int row, int m_tile, int col0,
-                                             int u0, const float* v) {
+__device__ __forceinline__ void finalize_gru(const Frame& fr, int t, int m, int row, int m_tile, int u0, const float* v,
+                                             const Prefetch& pf) {
     if (m >= fr.M) return;
     const int H = fr.H;
-    const float* gz = op.addend + (size_t)t * op.add_tstride + (size_t)m * op.ldadd + col0;
-    const float* gh = fr.gh + (size_t)m * 3 * H + col0;
-    float* hp = fr.h + (size_t)m * H + u0;
-    const float4 zr = __ldcg(reinterpret_cast<const float4*>(gz)), zz = __ldcg(reinterpret_cast<const float4*>(gz + 4));
-    const float4 zn = __ldcg(reinterpret_cast<const float4*>(gz + 8));
-    const float4 hr = __ldcg(reinterpret_cast<const float4*>(gh)), hz = __ldcg(reinterpret_cast<const float4*>(gh + 4));
-    const float4 hn4 = __ldcg(reinterpret_cast<const float4*>(gh + 8));
-    const float4 hv4 = *reinterpret_cast<const float4*>(hp);     // only this thread ever touches these 4 states
-    const float gzr[4] = {zr.x, zr.y, zr.z, zr.w}, gzz[4] = {zz.x, zz.y, zz.z, zz.w}, gzn[4] = {zn.x, zn.y, zn.z, zn.w};
-    const float ghr[4] = {hr.x, hr.y, hr.z, hr.w}, ghz[4] = {hz.x, hz.y, hz.z, hz.w}, ghn[4] = {hn4.x, hn4.y, hn4.z, hn4.w};
-    const float hv[4] = {hv4.x, hv4.y, hv4.z, hv4.w};
     float hn[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float rr = sigmoidf_(v[e] + gzr[e] + ghr[e]);
-        const float zg = sigmoidf_(v[4 + e] + gzz[e] + ghz[e]);
-        const float nn = tanhf(v[8 + e] + gzn[e] + rr * ghn[e]);
-        hn[e] = (hv[e] - nn) * zg + nn;
+        const float rr = sigmoidf_(v[e] + pf.a[e] + pf.b[e]);
+        const float zg = sigmoidf_(v[4 + e] + pf.a[4 + e] + pf.b[4 + e]);
+        const float nn = tanhf(v[8 + e] + pf.a[8 + e] + rr * pf.b[8 + e]);
+        hn[e] = (pf.b[12 + e] - nn) * zg + nn;
     }
-    if (fr.all_h)      // state entering frame t (bvrnn.py:205)
-        *reinterpret_cast<float4*>(fr.all_h + ((size_t)m * fr.T + t) * H + u0) = hv4;
-    *reinterpret_cast<float4*>(hp) = make_float4(hn[0], hn[1], hn[2], hn[3]);
     uint32_t h0, l0, h1, l1;
     split_pair(hn[0], hn[1], h0, l0);
     split_pair(hn[2], hn[3], h1, l1);
@@ -335,31 +348,153 @@ __device__ __forceinline__ void finalize_gru(const Op& op, const Frame& fr, int 
                           ((((u0 & 63) >> 3) ^ (row & 7)) << 4) + (u0 & 7) * 2;
     *reinterpret_cast<uint2*>(base) = make_uint2(h0, h1);
     *reinterpret_cast<uint2*>(base + ACT_PART_BYTES) = make_uint2(l0, l1);
+    *reinterpret_cast<float4*>(fr.h + (size_t)m * H + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    if (fr.all_h)      // state entering frame t (bvrnn.py:205)
+        *reinterpret_cast<float4*>(fr.all_h + ((size_t)m * fr.T + t) * H + u0) = make_float4(pf.b[12], pf.b[13], pf.b[14], pf.b[15]);
 }
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+          "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+          "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+          "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Reduce-scatter of one 128 x (4 QC) partial tile over the cluster.  acc = this CTA's partial row (4 QC columns);
+// returns in v the full-K sums of the QC columns this CTA owns.
+template <int QC>
+__device__ __forceinline__ void exchange(const float* acc, int rank, int row, uint32_t stg_send, uint32_t stg_full_bar, float* own) {
+#pragma unroll
+    for (int p = 0; p < CLUSTER; ++p) {
+        if (p == rank) continue;
+        const int ss = rank < p ? rank : rank - 1;
+        const uint32_t dst = map_to_cta(stg_send + ss * STG_SENDER_BYTES + row * 16, (uint32_t)p);
+        const uint32_t bar = map_to_cta(stg_full_bar, (uint32_t)p);
+#pragma unroll
+        for (int q4 = 0; q4 < QC / 4; ++q4)
+            st_async_f4(dst + q4 * 2048, bar, acc[QC * p + 4 * q4], acc[QC * p + 4 * q4 + 1], acc[QC * p + 4 * q4 + 2],
+                        acc[QC * p + 4 * q4 + 3]);
+    }
+#pragma unroll
+    for (int i = 0; i < QC; ++i)
+        own[i] = rank == 0 ? acc[i] : rank == 1 ? acc[QC + i] : rank == 2 ? acc[2 * QC + i] : acc[3 * QC + i];
+}
+// sum the four K quarters in fixed order 0,1,2,3 (bit-reproducible)
+template <int QC>
+__device__ __forceinline__ void reduce_parts(const float* own, int rank, int row, const unsigned char* stg_recv, float* v) {
+#pragma unroll
+    for (int p = 0; p < CLUSTER; ++p) {
+        float part[QC];
+        if (p == rank) {
+#pragma unroll
+            for (int i = 0; i < QC; ++i) part[i] = own[i];
+        } else {
+            const int ss = p < rank ? p : p - 1;
+            const unsigned char* src = stg_recv + ss * STG_SENDER_BYTES + row * 16;
+#pragma unroll
+            for (int q4 = 0; q4 < QC / 4; ++q4) {
+                const float4 a = *reinterpret_cast<const float4*>(src + q4 * 2048);
+                part[4 * q4] = a.x; part[4 * q4 + 1] = a.y; part[4 * q4 + 2] = a.z; part[4 * q4 + 3] = a.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < QC; ++i) v[i] = (p == 0) ? part[i] : v[i] + part[i];
+    }
+}
+
+// Per-CTA schedule, built once in shared memory so that no role chases pointers through L2 inside the time loop
+// (the cluster- and gpu-scope fences of the protocol invalidate L1 all the time).
+constexpr int MAX_MY_ENTRIES = 320;
+struct PhaseLocal {
+    const unsigned char* a_src;    // first activation chunk of this CTA (m-tile and K quarter applied)
+    int nck;                       // activation / weight chunks per entry for this CTA
+    int kc0;                       // first k-chunk
+    int k_chunks;                  // of the whole layer (weight image stride)
+    int n;                         // entries of this CTA
+    int e_off;                     // into Control::ent
+    int split;
+};
+struct Control {
+    Bars bars;
+    uint32_t tmem_slot;
+    uint32_t n_ops;
+    Op ops[MAX_OPS];
+    PhaseLocal ph[MAX_PHASES];
+    unsigned short ent[MAX_MY_ENTRIES];   // (op << 8) | n_tile
+};
+constexpr int CONTROL_BYTES = 3072;
+static_assert(sizeof(Control) <= CONTROL_BYTES, "control block must fit the 3 KiB in front of the operand buffers");
 
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(kThreads, 1)
 recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words) {
-    extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) Bars bars;
-    __shared__ uint32_t tmem_slot;
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    Control& ctl = *reinterpret_cast<Control*>(smem_dyn);
+    Bars& bars = ctl.bars;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_ctarank();
     const int cluster = blockIdx.x / CLUSTER;
     int* abort_flag = reinterpret_cast<int*>(sync_words);
-    // identical in every CTA of the cluster (same static layout), so mapa() of a local address names the peer's copy
-    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    // identical in every CTA of the cluster, so mapa() of a local address names the peer's copy
+    const uint32_t smem_base = smem_u32(smem_dyn) + CONTROL_BYTES;
+    unsigned char* smem_gen = smem_dyn + CONTROL_BYTES;
+
+    const Frame& fr = prog->frame;
+    const int T = fr.T, n_phases = prog->n_phases;
+    const int m_tile = prog->cluster_mtile[cluster];
+    const unsigned dom_ctas = (unsigned)prog->mtile_ctas[m_tile];
+    unsigned* counter = sync_words + 32 * (1 + m_tile);
+    unsigned long long* trace = prog->trace;
+    const int trace_frames = prog->trace_frames;
 
     if (tid == 0) {
         for (int i = 0; i < A_SLOTS; ++i) mbar_init(&bars.fullA[i], 1);
         for (int i = 0; i < W_SLOTS; ++i) { mbar_init(&bars.fullW[i], 1); mbar_init(&bars.emptyW[i], 1); }
         for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&bars.accFull[i], 1); mbar_init(&bars.accEmpty[i], 4); }
         mbar_init(&bars.aFree, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars.stgFull[i], 4 * (CLUSTER - 1)); mbar_init(&bars.stgEmpty[i], 4 * (CLUSTER - 1)); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars.stgFull[i], 1); mbar_init(&bars.stgEmpty[i], 4 * (CLUSTER - 1)); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        if ((smem_u32(smem_dyn) & 1023u) != 0) atomicCAS(abort_flag, 0, 90);   // SWIZZLE_128B operands need 1 KiB alignment
+        // this CTA's schedule
+        int n_e = 0;
+        for (int ph = 0; ph < n_phases; ++ph) {
+            const Phase& g = prog->phases[ph];
+            const int* es = prog->entry_start + ph * (prog->n_clusters + 1) + cluster;
+            const int eb = es[0], cnt = es[1] - es[0];
+            PhaseLocal& l = ctl.ph[ph];
+            l.split = g.split;
+            l.k_chunks = g.k_chunks;
+            l.nck = g.split ? g.k_chunks / CLUSTER : g.k_chunks;
+            l.kc0 = g.split ? rank * l.nck : 0;
+            l.a_src = g.a_img + ((size_t)m_tile * g.k_chunks + l.kc0) * ACT_CHUNK_BYTES;
+            l.e_off = n_e;
+            l.n = 0;
+            for (int i = g.split ? 0 : rank; i < cnt; i += g.split ? 1 : CLUSTER) {
+                const uint32_t e = prog->entries[eb + i];
+                if (n_e < MAX_MY_ENTRIES) ctl.ent[n_e] = (unsigned short)(((e >> 16) << 8) | (e & 0xFF));
+                ++n_e;
+                ++l.n;
+            }
+        }
+        if (n_e > MAX_MY_ENTRIES) atomicCAS(abort_flag, 0, 91);
+        ctl.n_ops = (uint32_t)prog->n_ops;
     }
+    for (int i = tid; i < prog->n_ops * (int)(sizeof(Op) / 4); i += kThreads)
+        reinterpret_cast<uint32_t*>(ctl.ops)[i] = reinterpret_cast<const uint32_t*>(prog->ops)[i];
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)),
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&ctl.tmem_slot)),
                      "r"((uint32_t)TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
     }
@@ -367,35 +502,30 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     __syncthreads();
     cluster_sync_all();          // peers' mbarriers are initialised before anyone signals them
     tc_fence_after();
-    const uint32_t tmem = tmem_slot;
+    const uint32_t tmem = ctl.tmem_slot;
+    const bool bad_setup = *(volatile int*)abort_flag != 0;
 
-    const Frame& fr = prog->frame;
-    const int T = fr.T, n_phases = prog->n_phases;
-    const int m_tile = prog->cluster_mtile[cluster];
-    const unsigned dom_ctas = (unsigned)prog->mtile_ctas[m_tile];
-    unsigned* counter = sync_words + 32 * (1 + m_tile);
-
-    if (warp == 1) {
+    if (bad_setup) {
+        // fall through to the common exit
+    } else if (warp == 1) {
         // =========================== copy thread ===========================
         if (lane == 0) {
             uint32_t wIt = 0, aIt = 0;
             bool dead = false;
             for (int t = 0; t < T && !dead; ++t) {
                 for (int ph = 0; ph < n_phases && !dead; ++ph) {
-                    const Phase& phs = prog->phases[ph];
-                    const JobView jv = my_entries(prog, ph, cluster, rank);
-                    const int nck = phs.split ? phs.k_chunks / CLUSTER : phs.k_chunks;
-                    const int kc0 = phs.split ? rank * nck : 0;
-                    const int nW = jv.n * nck;
+                    const PhaseLocal& pl = ctl.ph[ph];
+                    const int nck = pl.nck;
+                    const int nW = pl.n * nck;
                     auto issue_w = [&](int i) {
                         const int j = i / nck, c = i - j * nck;
-                        const uint32_t e = prog->entries[jv.e0 + j * jv.stride];
-                        const Op& op = prog->ops[e >> 16];
-                        const int nt = (int)(e & 0xFFFF);
+                        const uint32_t e = ctl.ent[pl.e_off + j];
+                        const Op& op = ctl.ops[e >> 8];
+                        const int nt = (int)(e & 0xFF);
                         const int slot = wIt % W_SLOTS, round = wIt / W_SLOTS;
                         if (round >= 1 && !mbar_wait<false>(&bars.emptyW[slot], (round - 1) & 1, abort_flag, 11)) { dead = true; return; }
                         const uint32_t bytes = 2u * op.bn * 128u;
-                        const unsigned char* src = op.w_img + ((size_t)nt * phs.k_chunks + kc0 + c) * bytes;
+                        const unsigned char* src = op.w_img + ((size_t)nt * pl.k_chunks + pl.kc0 + c) * bytes;
                         mbar_expect_tx(&bars.fullW[slot], bytes);
                         bulk_g2s(smem_base + SMEM_W + slot * W_SLOT_BYTES, src, bytes, &bars.fullW[slot]);
                         ++wIt;
@@ -403,7 +533,9 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     // weights do not depend on the previous phase: start them before waiting for it
                     const int pre = nW < W_SLOTS ? nW : W_SLOTS;
                     for (int i = 0; i < pre && !dead; ++i) issue_w(i);
-                    if (jv.n > 0 && !dead) {
+                    if (pl.n > 0 && !dead) {
+                        const unsigned char* src = pl.a_src;
+                        if (aIt >= 1 && !mbar_wait<false>(&bars.aFree, (aIt - 1) & 1, abort_flag, 12)) dead = true;
                         const unsigned target = (unsigned)(t * n_phases + ph) * dom_ctas;
                         if (ld_acquire(counter) < target) {
                             const long long t0 = clock64();
@@ -415,11 +547,9 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                                 }
                             }
                         }
-                        if (prog->debug_flags & 16) { const long long d0 = clock64(); while (clock64() - d0 < 100000) {} }
+                        BVC_TRACE(2);
                         fence_proxy_async_all();   // the producers' generic-proxy stores -> this thread's async-proxy reads
-                        if (!dead && aIt >= 1 && !mbar_wait<false>(&bars.aFree, (aIt - 1) & 1, abort_flag, 12)) dead = true;
                         if (!dead) {
-                            const unsigned char* src = phs.a_img + ((size_t)m_tile * phs.k_chunks + kc0) * ACT_CHUNK_BYTES;
                             for (int c = 0; c < nck; ++c) {
                                 mbar_expect_tx(&bars.fullA[c], ACT_CHUNK_BYTES);
                                 bulk_g2s(smem_base + SMEM_A + c * ACT_CHUNK_BYTES, src + (size_t)c * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES,
@@ -427,8 +557,10 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             }
                             ++aIt;
                         }
+                        BVC_TRACE(3);
                     }
                     for (int i = pre; i < nW && !dead; ++i) issue_w(i);
+                    BVC_TRACE(4);
                 }
             }
         }
@@ -442,12 +574,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
             const uint64_t descA = make_desc(smem_base + SMEM_A), descW = make_desc(smem_base + SMEM_W);
             for (int t = 0; t < T && !dead; ++t) {
                 for (int ph = 0; ph < n_phases && !dead; ++ph) {
-                    const Phase& phs = prog->phases[ph];
-                    const JobView jv = my_entries(prog, ph, cluster, rank);
-                    const int nck = phs.split ? phs.k_chunks / CLUSTER : phs.k_chunks;
-                    for (int j = 0; j < jv.n && !dead; ++j) {
-                        const uint32_t e = prog->entries[jv.e0 + j * jv.stride];
-                        const int bn = prog->ops[e >> 16].bn;
+                    const PhaseLocal& pl = ctl.ph[ph];
+                    const int nck = pl.nck;
+                    for (int j = 0; j < pl.n && !dead; ++j) {
+                        const uint32_t e = ctl.ent[pl.e_off + j];
+                        const int bn = ctl.ops[e >> 8].bn;
                         const int slot = accIt % ACC_SLOTS, round = accIt / ACC_SLOTS;
                         if (round >= 1 && !mbar_wait<false>(&bars.accEmpty[slot], (round - 1) & 1, abort_flag, 21)) { dead = true; break; }
                         tc_fence_after();
@@ -457,6 +588,8 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             if (j == 0) {
                                 if (!mbar_wait<false>(&bars.fullA[c], aUse[c] & 1, abort_flag, 22)) { dead = true; break; }
                                 ++aUse[c];
+                                if (c == 0) BVC_TRACE(5);
+                                if (c == nck - 1) BVC_TRACE(6);
                             }
                             const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
                             if (!mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
@@ -478,7 +611,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         umma_commit(&bars.accFull[slot]);
                         ++accIt;
                     }
-                    if (jv.n > 0 && !dead) umma_commit(&bars.aFree);
+                    if (pl.n > 0 && !dead) { umma_commit(&bars.aFree); BVC_TRACE(7); }
                 }
             }
         }
@@ -489,100 +622,70 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
         const int row = quad * 32 + lane;              // row of the m-tile this thread owns
         const int m = m_tile * TILE_M + row;
         const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-        const uint32_t stg_local = smem_base + SMEM_STG;
         uint32_t accIt = 0, sIt = 0;
         bool dead = false;
         for (int t = 0; t < T && !dead; ++t) {
             for (int ph = 0; ph < n_phases && !dead; ++ph) {
-                const Phase& phs = prog->phases[ph];
-                const JobView jv = my_entries(prog, ph, cluster, rank);
-                for (int j = 0; j < jv.n && !dead; ++j) {
-                    const uint32_t e = prog->entries[jv.e0 + j * jv.stride];
-                    const Op& op = prog->ops[e >> 16];
-                    const int nt = (int)(e & 0xFFFF);
+                const PhaseLocal& pl = ctl.ph[ph];
+                for (int j = 0; j < pl.n && !dead; ++j) {
+                    const uint32_t e = ctl.ent[pl.e_off + j];
+                    const Op& op = ctl.ops[e >> 8];
+                    const int nt = (int)(e & 0xFF);
+                    const int qc = op.bn >> 2;         // columns per CTA after the reduce-scatter: 16 or 12
+                    const int col0 = pl.split ? nt * op.bn + qc * rank : nt * op.bn;
+                    const int u0 = nt * 16 + 4 * rank; // GRU: first of this thread's 4 hidden units
+                    Prefetch pf;
+                    prefetch_epilogue(op, fr, t, m, col0, u0, pf);
                     const int slot = accIt % ACC_SLOTS, round = accIt / ACC_SLOTS;
                     if (!mbar_wait<false>(&bars.accFull[slot], round & 1, abort_flag, 31)) { dead = true; break; }
                     ++accIt;
+                    if (tid == 128 && j == 0) BVC_TRACE(8);
+                    if (tid == 128 && j == pl.n - 1) BVC_TRACE(9);
                     tc_fence_after();
                     const uint32_t taddr = t_lane + slot * ACC_COLS;
                     float v[16];
-                    int col0;
-                    if (phs.split) {
-                        const int qc = op.bn >> 2;                       // columns per CTA after the reduce-scatter: 16 or 12
+                    if (pl.split) {
                         const int buf = sIt & 1, sr = sIt >> 1;
                         ++sIt;
+                        float acc[64], own[16];
+                        tmem_ld64(taddr, acc);
+                        tc_fence_before();
+                        if (tid == 128 && j == pl.n - 1) BVC_TRACE(10);
                         // my staging slot at every peer is free once all peers have read their copy of two tiles ago
                         if (sr >= 1 && !mbar_wait<false>(&bars.stgEmpty[buf], (sr - 1) & 1, abort_flag, 32)) { dead = true; break; }
-                        float own[16];
-#pragma unroll
-                        for (int p = 0; p < CLUSTER; ++p) {
-                            if (p == rank) {
-                                tmem_ld16(taddr + qc * p, own);
-                            } else {
-                                float tmp[16];
-                                tmem_ld16(taddr + qc * p, tmp);
-                                const int ss = rank < p ? rank : rank - 1;
-                                const uint32_t dst =
-                                    map_to_cta(stg_local + buf * STG_BUF_BYTES + ss * STG_SENDER_BYTES + row * 16, (uint32_t)p);
-                                st_cluster_f4(dst, tmp[0], tmp[1], tmp[2], tmp[3]);
-                                st_cluster_f4(dst + 2048, tmp[4], tmp[5], tmp[6], tmp[7]);
-                                st_cluster_f4(dst + 4096, tmp[8], tmp[9], tmp[10], tmp[11]);
-                                if (qc == 16) st_cluster_f4(dst + 6144, tmp[12], tmp[13], tmp[14], tmp[15]);
-                            }
-                        }
-                        tc_fence_before();
+                        const uint32_t stg_send = smem_base + SMEM_STG + buf * STG_BUF_BYTES;
+                        const unsigned char* stg_recv = smem_gen + SMEM_STG + buf * STG_BUF_BYTES;
+                        // arm my own staging barrier for the 3 x 128 x qc floats the peers will store (st.async complete_tx)
+                        if (tid == 128) mbar_expect_tx(&bars.stgFull[buf], (uint32_t)((CLUSTER - 1) * TILE_M * qc * 4));
+                        if (qc == 16) exchange<16>(acc, rank, row, stg_send, smem_u32(&bars.stgFull[buf]), own);
+                        else exchange<12>(acc, rank, row, stg_send, smem_u32(&bars.stgFull[buf]), own);
+                        if (tid == 128 && j == pl.n - 1) BVC_TRACE(0);
                         __syncwarp();
-                        if (lane == 0) {
-                            mbar_arrive(&bars.accEmpty[slot]);
-                            fence_cluster();
-#pragma unroll
-                            for (int p = 0; p < CLUSTER; ++p)
-                                if (p != rank) mbar_arrive_remote(map_to_cta(smem_u32(&bars.stgFull[buf]), (uint32_t)p));
-                        }
-                        if (!mbar_wait<true>(&bars.stgFull[buf], sr & 1, abort_flag, 33)) { dead = true; break; }
-                        // sum the four K quarters in fixed order 0,1,2,3 (bit-reproducible)
-#pragma unroll
-                        for (int p = 0; p < CLUSTER; ++p) {
-                            float part[16];
-                            if (p == rank) {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) part[i] = own[i];
-                            } else {
-                                const int ss = p < rank ? p : p - 1;
-                                const unsigned char* src = smem_dyn + (smem_base - smem_u32(smem_dyn)) + SMEM_STG + buf * STG_BUF_BYTES +
-                                                           ss * STG_SENDER_BYTES + row * 16;
-#pragma unroll
-                                for (int q4 = 0; q4 < 4; ++q4) {
-                                    if (q4 < 3 || qc == 16) {
-                                        const float4 a = *reinterpret_cast<const float4*>(src + q4 * 2048);
-                                        part[4 * q4] = a.x; part[4 * q4 + 1] = a.y; part[4 * q4 + 2] = a.z; part[4 * q4 + 3] = a.w;
-                                    } else {
-                                        part[12] = part[13] = part[14] = part[15] = 0.f;
-                                    }
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = (p == 0) ? part[i] : v[i] + part[i];
-                        }
+                        if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
+                        if (tid == 128 && j == pl.n - 1) BVC_TRACE(11);
+                        if (!mbar_wait<false>(&bars.stgFull[buf], sr & 1, abort_flag, 33)) { dead = true; break; }
+                        if (tid == 128 && j == pl.n - 1) BVC_TRACE(14);
+                        if (qc == 16) reduce_parts<16>(own, rank, row, stg_recv, v);
+                        else reduce_parts<12>(own, rank, row, stg_recv, v);
+                        if (tid == 128 && j == pl.n - 1) BVC_TRACE(15);
                         __syncwarp();
                         if (lane == 0) {
 #pragma unroll
                             for (int p = 0; p < CLUSTER; ++p)
-                                if (p != rank) mbar_arrive_remote(map_to_cta(smem_u32(&bars.stgEmpty[buf]), (uint32_t)p));
+                                if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty[buf]), (uint32_t)p));
                         }
-                        col0 = nt * op.bn + qc * rank;
+                        if (tid == 128 && j == pl.n - 1) BVC_TRACE(1);
                     } else {
                         tmem_ld16(taddr, v);
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
-                        col0 = nt * op.bn;
                     }
-                    if (op.kind == KIND_GRU) finalize_gru(op, fr, t, m, row, m_tile, col0, nt * 16 + 4 * rank, v);
-                    else finalize16(op, fr, t, m, row, m_tile, col0, v);
+                    if (op.kind == KIND_GRU) finalize_gru(fr, t, m, row, m_tile, u0, v, pf);
+                    else finalize16(op, fr, t, m, row, m_tile, col0, v, pf);
                 }
                 // ---- end of phase: publish this CTA's outputs to the m-tile's barrier domain ----
-                if (prog->debug_flags & 32) __threadfence();
+                if (tid == 128) BVC_TRACE(12);
                 fence_proxy_async_all();                                  // they are read by other CTAs' bulk copies
                 {   // barrier over the 4 epilogue warps; a failed wait anywhere retires all of them together
                     uint32_t any;
@@ -600,7 +703,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     // The counter is monotonic over all phases, so nobody may arrive for phase p before every CTA
                     // of the domain has arrived for phase p - 1.  A CTA with work in phase p got that from its
                     // copy thread (which waited for it before loading activations); an idle CTA waits here.
-                    if (jv.n == 0) {
+                    if (pl.n == 0) {
                         const unsigned target = (unsigned)(t * n_phases + ph) * dom_ctas;
                         const long long t0 = clock64();
                         int spins = 0;
@@ -613,6 +716,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         }
                     }
                     asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
+                    BVC_TRACE(13);
                 }
             }
         }

@@ -1,0 +1,38 @@
+"""Reads a BVC_REC_TRACE dump of the recurrent kernel and prints a per-phase timeline of one frame.
+
+    BVC_REC_TRACE=/tmp/t.bin python tools/run_recurrent_once.py ... ; python tools/trace_report.py /tmp/t.bin [frame]
+
+Events (ns, %globaltimer): copy thread 0 phase start, 1 weight prefetch issued, 2 phase barrier passed, 3 activations
+issued, 4 all weights issued; MMA thread 5 first activation chunk landed, 6 last chunk landed, 7 last MMA issued;
+epilogue 8 first accumulator complete, 9 last accumulator complete, 10 last accumulator read from TMEM, 11 last partials
+sent and signalled, 14 peers' partials received, 15 partials summed, 12 last tile finalised, 13 arrived at the phase barrier.
+"""
+import sys
+import numpy as np
+
+path = sys.argv[1]
+frame = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+hdr = np.fromfile(path, dtype=np.int32, count=4)
+n_cta, n_fr, n_ph, n_ev = [int(v) for v in hdr]
+d = np.fromfile(path, dtype=np.uint64, offset=16).reshape(n_cta, n_fr, n_ph, n_ev).astype(np.float64)
+d[d == 0] = np.nan
+fr = d[:, frame]
+prev_done = np.nanmax(d[:, frame - 1, :, 13]) if frame > 0 else np.nanmin(fr[:, 0, 0])
+order = [2, 3, 4, 5, 6, 7, 8, 9, 10, 0, 11, 14, 15, 1, 12, 13]
+names = ["bar", "Aiss", "Wall", "A0", "Alast", "mma", "acc0", "accL", "tmem", "stores", "sent", "recv", "sum", "freed", "fin", "arr"]
+print("frame %d: %d CTAs; times in us relative to the previous phase's last barrier arrival" % (frame, n_cta))
+print("phase  dur   busy | " + " ".join("%6s" % n for n in names) + "   (median over busy CTAs)   last-arr-cta")
+total = 0.0
+for ph in range(n_ph):
+    if np.all(np.isnan(fr[:, ph, 13])):
+        continue
+    done = np.nanmax(fr[:, ph, 13])
+    busy = ~np.isnan(fr[:, ph, 8])
+    med = [np.nanmedian(fr[busy, ph, e]) - prev_done if busy.any() else np.nan for e in order]
+    mx = [np.nanmax(fr[busy, ph, e]) - prev_done if busy.any() else np.nan for e in order]
+    print("%3d  %6.2f  %4d | " % (ph, (done - prev_done) / 1e3, int(busy.sum())) + " ".join("%6.2f" % (v / 1e3) for v in med) +
+          "   cta %d" % int(np.nanargmax(fr[:, ph, 13])))
+    print("                  max " + " ".join("%6.2f" % (v / 1e3) for v in mx))
+    total += (done - prev_done) / 1e3
+    prev_done = done
+print("frame total %.2f us" % total)
