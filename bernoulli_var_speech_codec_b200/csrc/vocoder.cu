@@ -229,11 +229,18 @@ __global__ void __launch_bounds__(kThreads, 1) stage_fp32_kernel(StageArgs a) {
 }
 
 // ===========================================================================
-// precision 1: tensor-core stage kernel
+// precision 1: tensor-core stage kernel, streaming over time
 // ===========================================================================
+// A CTA owns (utterance b, resblock kernel size K, a contiguous time range) and walks that range in tiles of TT
+// output samples.  All convolutions are causal, so the only coupling between consecutive tiles is the left
+// context of each conv input: (K-1) d rows for the dilated conv of layer l, K-1 rows for its second conv.  Those
+// rows are kept in shared memory from one tile to the next (6 small context buffers), so no sample is ever
+// computed twice; a range that starts inside the utterance warms its contexts up on the 12 (K-1) samples before it.
 template <int C>
 struct RowLayout {
-    static constexpr int PW = C >= 16 ? C / 2 + 4 : C / 2;   // uint32 (bf16 pair) words per activation row
+    static constexpr int PW = C >= 16 ? C / 2 + 4 : C / 2;   // uint32 (bf16 pair) words per activation row; rows are
+                                                             // 16-byte aligned and 8 consecutive rows hit 8 distinct
+                                                             // 16-byte bank groups (conflict-free ldmatrix)
     static constexpr int PF = C + 8;                         // floats per residual row
 };
 
@@ -242,6 +249,11 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_addr));
 }
 
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -252,55 +264,72 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
     lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
 }
 
-// One warp computes a 32-row x COUT tile of  out[row][co] = sum_{tap,ci} in[row - (NTAPS-1-tap) d][ci] W[tap][ci][co].
-// inh/inl: split-bf16 activation rows (pitch RowLayout<CIN>::PW words); rows are clamped to [0, max_row].
-// wh/wl: fragment-packed weights.  epi(row, co, v0, v1) receives channels (co, co+1) of one row.
-template <int CIN, int COUT, int NTAPS, typename Epi>
-__device__ __forceinline__ void mma_tile32(const uint32_t* __restrict__ inh, const uint32_t* __restrict__ inl,
-                                           int max_row, const uint2* __restrict__ wh, const uint2* __restrict__ wl,
-                                           int d, int r0, Epi epi) {
-    constexpr int PW = RowLayout<CIN>::PW;
+// One warp computes a (16 MT)-row x COUT tile of  out[r][co] = sum_{tap,ci} in[r + lead - (NTAPS-1-tap) d][ci] W[tap][ci][co]
+// for r = r0 .. r0 + 16 MT - 1.  inh/inl: shared-memory byte addresses of the split-bf16 activation rows (pitch
+// RowLayout<CIN>::PW words); `lead` = index of the buffer row that holds output row 0's undelayed input.
+// wh/wl: fragment-packed weights.  epi(r, co, v0, v1) receives channels (co, co+1) of output row r.
+template <int CIN, int COUT, int NTAPS, int MT, typename Epi>
+__device__ __forceinline__ void mma_rows(uint32_t inh, uint32_t inl, int lead, const uint2* __restrict__ wh,
+                                         const uint2* __restrict__ wl, int d, int r0, Epi epi) {
+    constexpr int PWB = RowLayout<CIN>::PW * 4;     // row pitch in bytes
     constexpr int NT = COUT / 8;
     constexpr int KC = (NTAPS * CIN + 15) / 16;
     const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    float acc[2][NT][4];
+    // ldmatrix: lane -> (matrix mi = lane / 8, row rr = lane % 8); matrices 0..3 = (rows 0-7 | 8-15) x (k 0-7 | 8-15)
+    const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lkh = lane >> 4;
+    float acc[MT][NT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
 
+    // weight fragments are fetched one k16 chunk ahead (they come from L1 / L2: long-scoreboard latency), and the
+    // three split-bf16 terms are issued term-major so that consecutive MMAs never target the same accumulator
+    uint2 bh[NT], bl[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        bh[nt] = __ldg(wh + nt * 32 + lane);
+        bl[nt] = __ldg(wl + nt * 32 + lane);
+    }
 #pragma unroll 2
     for (int kc = 0; kc < KC; ++kc) {
-        const int k_lo = 16 * kc + 2 * q, k_hi = k_lo + 8;
-        const int tap_lo = k_lo / CIN, tap_hi = k_hi / CIN;
-        const int w_lo = (k_lo % CIN) >> 1, w_hi = (k_hi % CIN) >> 1;
-        const int off_lo = tap_lo < NTAPS ? (NTAPS - 1 - tap_lo) * d : 0;
-        const int off_hi = tap_hi < NTAPS ? (NTAPS - 1 - tap_hi) * d : 0;
-        uint32_t ah[2][4], al[2][4];
+        const int kk = 16 * kc + 8 * lkh;           // first GEMM-K index of this lane's 8x8 matrix
+        const int tap = kk / CIN, ci = kk % CIN;
+        const int off = tap < NTAPS ? (NTAPS - 1 - tap) * d : 0;   // K padding (zero weights): any valid row
+        const int rbase = r0 + lead + lrow - off;
+        uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            const int ra = r0 + mt * 16 + g, rb = ra + 8;
-            const int i0 = min(ra - off_lo, max_row) * PW + w_lo, i1 = min(rb - off_lo, max_row) * PW + w_lo;
-            const int i2 = min(ra - off_hi, max_row) * PW + w_hi, i3 = min(rb - off_hi, max_row) * PW + w_hi;
-            ah[mt][0] = inh[i0]; ah[mt][1] = inh[i1]; ah[mt][2] = inh[i2]; ah[mt][3] = inh[i3];
-            al[mt][0] = inl[i0]; al[mt][1] = inl[i1]; al[mt][2] = inl[i2]; al[mt][3] = inl[i3];
+        for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t o = (uint32_t)((rbase + mt * 16) * PWB + ci * 2);
+            ldmatrix_x4(ah[mt], inh + o);
+            ldmatrix_x4(al[mt], inl + o);
         }
+        uint2 nh[NT], nl[NT];
+        const int kn = kc + 1 < KC ? kc + 1 : kc;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-            const uint2 bh = __ldg(wh + (kc * NT + nt) * 32 + lane);
-            const uint2 bl = __ldg(wl + (kc * NT + nt) * 32 + lane);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                mma16816(acc[mt][nt], al[mt], bh);
-                mma16816(acc[mt][nt], ah[mt], bl);
-                mma16816(acc[mt][nt], ah[mt], bh);
-            }
+            nh[nt] = __ldg(wh + (kn * NT + nt) * 32 + lane);
+            nl[nt] = __ldg(wl + (kn * NT + nt) * 32 + lane);
         }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma16816(acc[mt][nt], al[mt], bh[nt]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma16816(acc[mt][nt], ah[mt], bl[nt]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma16816(acc[mt][nt], ah[mt], bh[nt]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { bh[nt] = nh[nt]; bl[nt] = nl[nt]; }
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const int row = r0 + mt * 16 + g, co = nt * 8 + 2 * q;
@@ -309,151 +338,194 @@ __device__ __forceinline__ void mma_tile32(const uint32_t* __restrict__ inh, con
         }
 }
 
-template <int C, int U, int K>
-__global__ void __launch_bounds__(kThreads, 1) stage_mma_kernel(StageArgs a) {
+template <int C, int K>
+struct StreamLayout {
+    static constexpr int PW = RowLayout<C>::PW, PF = RowLayout<C>::PF;
+    static constexpr int CTX1 = (K - 1) * 5;       // rows in front of the dilated conv's input tile (largest dilation)
+    static constexpr int CTX2 = K - 1;
+    static constexpr int CTXSUM = (K - 1) * 9;     // (K-1)(1+3+5) saved rows for the three dilated convs
+    // shared memory in 32-bit words for a tile of TT rows (+16 spare rows so that partial warp tiles stay in bounds)
+    static constexpr size_t words(int TT) {
+        return (size_t)(TT + 16) * PF + 2 * (size_t)(CTX1 + TT + 16) * PW + 2 * (size_t)(CTX2 + TT + 16) * PW +
+               2 * (size_t)CTXSUM * PW + 2 * (size_t)3 * CTX2 * PW;
+    }
+};
+
+template <int C, int U, int K, int MT>
+__global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
     constexpr int CIN = 2 * C;
     constexpr int HALO = 12 * (K - 1);
-    constexpr int PW = RowLayout<C>::PW, PF = RowLayout<C>::PF, PWI = RowLayout<CIN>::PW;
+    constexpr int HALOR = ((HALO + U - 1) / U) * U;
+    using L = StreamLayout<C, K>;
+    constexpr int PW = L::PW, PF = L::PF, PWI = RowLayout<CIN>::PW, CTX1 = L::CTX1, CTX2 = L::CTX2;
+    constexpr int RW = 16 * MT;                    // rows per warp tile
     extern __shared__ __align__(16) float smem[];
     const int TT = a.TT;
-    const int W = TT + HALO;
-    float* cur = smem;                                            // [W][PF] fp32 residual stream
-    uint32_t* s1h = reinterpret_cast<uint32_t*>(cur + W * PF);    // [W][PW] conv1 input (hi)
-    uint32_t* s1l = s1h + W * PW;
-    uint32_t* s2h = s1l + W * PW;                                 // [W][PW] conv2 input
-    uint32_t* s2l = s2h + W * PW;
-    const int NJ = W / U + 2;
-    uint32_t* xh = s1h;                                           // [NJ][PWI] stage input tile (aliases s1/s2)
-    uint32_t* xl = xh + NJ * PWI;
+    float* cur = smem;                                                   // [TT+16][PF] fp32 residual stream
+    uint32_t* s1h = reinterpret_cast<uint32_t*>(cur + (TT + 16) * PF);   // [CTX1+TT+16][PW] dilated conv input (hi)
+    uint32_t* s1l = s1h + (CTX1 + TT + 16) * PW;
+    uint32_t* s2h = s1l + (CTX1 + TT + 16) * PW;                         // [CTX2+TT+16][PW] second conv input
+    uint32_t* s2l = s2h + (CTX2 + TT + 16) * PW;
+    uint32_t* c1h = s2l + (CTX2 + TT + 16) * PW;                         // saved contexts of the 3 dilated convs
+    uint32_t* c1l = c1h + L::CTXSUM * PW;
+    uint32_t* c2h = c1l + L::CTXSUM * PW;                                // [3][CTX2] saved contexts of the second convs
+    uint32_t* c2l = c2h + 3 * CTX2 * PW;
+    const int NJ = TT / U + 1;                                           // low-rate rows j0-1 .. j0+TT/U-1
+    uint32_t* xh = s1h;                                                  // [NJ+16][PWI] stage input tile (aliases s1)
+    uint32_t* xl = xh + (NJ + 16) * PWI;
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int b = blockIdx.y;
-    const int t0 = blockIdx.x * TT;
-    const int tg0 = t0 - HALO;
-    const int j_base = tg0 / U - 1;
+    // this CTA's time range [t_begin, t_end) of the stage output, tile-aligned
+    const int tiles_total = (a.n_out + TT - 1) / TT;
+    const int tiles_per = (tiles_total + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * tiles_per * TT;
+    const int t_end = min(a.n_out, t_begin + tiles_per * TT);
+    if (t_begin >= t_end) return;
+    const int t_first = max(0, t_begin - ((HALOR + TT - 1) / TT) * TT);  // warm-up tiles (outputs discarded)
 
-    // ---- stage input tile: mean of the producer's partials, split to bf16 hi/lo ----
-    {
-        const size_t boff = (size_t)b * a.in_bstride;
-        constexpr int V = CIN / 4;
-        for (int i = tid; i < NJ * V; i += kThreads) {
-            const int jj = i / V, c4 = i - jj * V;
-            const int j = j_base + jj;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j >= 0 && j < a.n_in) {
-                const size_t o = boff + (size_t)j * CIN + c4 * 4;
-                v = __ldg(reinterpret_cast<const float4*>(a.in_p[0] + o));
-                if (a.n_parts == 3) {
-                    const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.in_p[1] + o));
-                    const float4 v2 = __ldg(reinterpret_cast<const float4*>(a.in_p[2] + o));
-                    v.x = ((v.x + v1.x) + v2.x) / 3.0f; v.y = ((v.y + v1.y) + v2.y) / 3.0f;
-                    v.z = ((v.z + v1.z) + v2.z) / 3.0f; v.w = ((v.w + v1.w) + v2.w) / 3.0f;
-                }
-            }
-            uint32_t h0, l0, h1, l1;
-            split_pair(v.x, v.y, h0, l0);
-            split_pair(v.z, v.w, h1, l1);
-            *reinterpret_cast<uint2*>(xh + jj * PWI + c4 * 2) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(xl + jj * PWI + c4 * 2) = make_uint2(l0, l1);
-        }
-    }
+    for (int i = tid; i < 2 * (L::CTXSUM + 3 * CTX2) * PW; i += kThreads) c1h[i] = 0u;   // causal zero history
     __syncthreads();
 
-    // ---- ConvTranspose1d as U phase convolutions: phase r is a 2-tap conv over (x[j-1], x[j]) ----
-    {
-        constexpr int KC_UP = (2 * CIN) / 16, NT = C / 8;
-        const int rows = W / U;                      // low-rate rows m in [0, rows): output position p = U m + r
-        const int tiles = (rows + 31) / 32;
-        for (int item = warp; item < U * tiles; item += kThreads / 32) {
-            const int r = item / tiles, tile = item - r * tiles;
-            const uint2* wh = a.upf_h + (size_t)r * KC_UP * NT * 32;
-            const uint2* wl = a.upf_l + (size_t)r * KC_UP * NT * 32;
-            mma_tile32<CIN, C, 2>(xh, xl, NJ - 1, wh, wl, 1, 1 + tile * 32, [&](int row, int co, float v0, float v1) {
-                const int p = U * (row - 1) + r;
-                if (row - 1 < rows)
-                    *reinterpret_cast<float2*>(cur + p * PF + co) =
-                        make_float2(v0 + __ldg(a.b_up + co), v1 + __ldg(a.b_up + co + 1));
-            });
-        }
-    }
-    __syncthreads();   // xh/xl are dead from here on
-
-    // ---- AMP block ----
-    int lo = 0;
-#pragma unroll 1
-    for (int l = 0; l < 3; ++l) {
-        const int d = a.dil[l];
-        {
-            const float* ea = a.ea[2 * l];
-            const float* ieb = a.ieb[2 * l];
-            constexpr int CP = C / 2;
-            for (int i = tid; i < (W - lo) * CP; i += kThreads) {
-                const int row = lo + i / CP, cp = i % CP;
-                const float2 v = *reinterpret_cast<const float2*>(cur + row * PF + 2 * cp);
-                float y0 = 0.f, y1 = 0.f;
-                if (tg0 + row >= 0) {
-                    y0 = snake(v.x, __ldg(ea + 2 * cp), __ldg(ieb + 2 * cp));
-                    y1 = snake(v.y, __ldg(ea + 2 * cp + 1), __ldg(ieb + 2 * cp + 1));
-                }
-                uint32_t hi, lw;
-                split_pair(y0, y1, hi, lw);
-                s1h[row * PW + cp] = hi;
-                s1l[row * PW + cp] = lw;
-            }
-        }
-        __syncthreads();
-        const int lo1 = lo + (K - 1) * d;
-        {
-            const float* ea = a.ea[2 * l + 1];
-            const float* ieb = a.ieb[2 * l + 1];
-            const float* bias = a.b1[l];
-            const int tiles = (W - lo1 + 31) / 32;
-            for (int tile = warp; tile < tiles; tile += kThreads / 32) {
-                mma_tile32<C, C, K>(s1h, s1l, W - 1, a.f1h[l], a.f1l[l], d, lo1 + tile * 32,
-                                    [&](int row, int co, float v0, float v1) {
-                                        if (row >= W) return;
-                                        float y0 = 0.f, y1 = 0.f;
-                                        if (tg0 + row >= 0) {
-                                            y0 = snake(v0 + __ldg(bias + co), __ldg(ea + co), __ldg(ieb + co));
-                                            y1 = snake(v1 + __ldg(bias + co + 1), __ldg(ea + co + 1), __ldg(ieb + co + 1));
-                                        }
-                                        uint32_t hi, lw;
-                                        split_pair(y0, y1, hi, lw);
-                                        s2h[row * PW + (co >> 1)] = hi;
-                                        s2l[row * PW + (co >> 1)] = lw;
-                                    });
-            }
-        }
-        __syncthreads();
-        const int lo2 = lo1 + (K - 1);
-        {
-            const float* bias = a.b2[l];
-            const int tiles = (W - lo2 + 31) / 32;
-            for (int tile = warp; tile < tiles; tile += kThreads / 32) {
-                mma_tile32<C, C, K>(s2h, s2l, W - 1, a.f2h[l], a.f2l[l], 1, lo2 + tile * 32,
-                                    [&](int row, int co, float v0, float v1) {
-                                        if (row >= W) return;
-                                        float2* p = reinterpret_cast<float2*>(cur + row * PF + co);
-                                        float2 c = *p;
-                                        c.x += v0 + __ldg(bias + co);
-                                        c.y += v1 + __ldg(bias + co + 1);
-                                        *p = c;
-                                    });
-            }
-        }
-        __syncthreads();
-        lo = lo2;
-    }
-
-    // ---- write the tile (rows [HALO, W)), channel-last, coalesced ----
+    const size_t boff = (size_t)b * a.in_bstride;
     float* dst = a.out + (size_t)b * a.n_out * C;
-    constexpr int V = C / 4;
-    for (int i = tid; i < TT * V; i += kThreads) {
-        const int tt = i / V, c4 = i - tt * V;
-        const int tg = t0 + tt;
-        if (tg < a.n_out)
-            *reinterpret_cast<float4*>(dst + (size_t)tg * C + c4 * 4) =
-                *reinterpret_cast<const float4*>(cur + (HALO + tt) * PF + c4 * 4);
+
+#pragma unroll 1
+    for (int t0 = t_first; t0 < t_end; t0 += TT) {
+        // ---- stage input rows j0-1 .. j0+TT/U-1: mean of the producer's partials, split to bf16 hi/lo ----
+        {
+            const int j_base = t0 / U - 1;
+            constexpr int V = CIN / 4;
+            for (int i = tid; i < NJ * V; i += kThreads) {
+                const int jj = i / V, c4 = i - jj * V;
+                const int j = j_base + jj;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j >= 0 && j < a.n_in) {
+                    const size_t o = boff + (size_t)j * CIN + c4 * 4;
+                    v = __ldg(reinterpret_cast<const float4*>(a.in_p[0] + o));
+                    if (a.n_parts == 3) {
+                        const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.in_p[1] + o));
+                        const float4 v2 = __ldg(reinterpret_cast<const float4*>(a.in_p[2] + o));
+                        v.x = ((v.x + v1.x) + v2.x) / 3.0f; v.y = ((v.y + v1.y) + v2.y) / 3.0f;
+                        v.z = ((v.z + v1.z) + v2.z) / 3.0f; v.w = ((v.w + v1.w) + v2.w) / 3.0f;
+                    }
+                }
+                uint32_t h0, l0, h1, l1;
+                split_pair(v.x, v.y, h0, l0);
+                split_pair(v.z, v.w, h1, l1);
+                *reinterpret_cast<uint2*>(xh + jj * PWI + c4 * 2) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(xl + jj * PWI + c4 * 2) = make_uint2(l0, l1);
+            }
+        }
+        __syncthreads();
+
+        // ---- ConvTranspose1d as U phase convolutions: phase r is a 2-tap conv over (x[j-1], x[j]) ----
+        {
+            const int rows = TT / U;                    // low-rate rows m: output position p = U m + r
+            const int tiles = (rows + RW - 1) / RW;
+            const uint32_t xh_a = (uint32_t)__cvta_generic_to_shared(xh), xl_a = (uint32_t)__cvta_generic_to_shared(xl);
+            constexpr int KC_UP = (2 * CIN) / 16, NT = C / 8;
+            for (int item = warp; item < U * tiles; item += kThreads / 32) {
+                const int r = item / tiles, tile = item - r * tiles;
+                const uint2* wh = a.upf_h + (size_t)r * KC_UP * NT * 32;
+                const uint2* wl = a.upf_l + (size_t)r * KC_UP * NT * 32;
+                mma_rows<CIN, C, 2, MT>(xh_a, xl_a, 1, wh, wl, 1, tile * RW, [&](int row, int co, float v0, float v1) {
+                    if (row < rows)
+                        *reinterpret_cast<float2*>(cur + (U * row + r) * PF + co) =
+                            make_float2(v0 + __ldg(a.b_up + co), v1 + __ldg(a.b_up + co + 1));
+                });
+            }
+        }
+        __syncthreads();   // xh/xl (aliasing s1) are dead from here on
+
+        // ---- AMP block: 3 x (snake, dilated conv, snake, conv, residual) ----
+        const uint32_t s1h_a = (uint32_t)__cvta_generic_to_shared(s1h), s1l_a = (uint32_t)__cvta_generic_to_shared(s1l);
+        const uint32_t s2h_a = (uint32_t)__cvta_generic_to_shared(s2h), s2l_a = (uint32_t)__cvta_generic_to_shared(s2l);
+        const int tiles = (TT + RW - 1) / RW;
+        int c1off = 0;
+#pragma unroll 1
+        for (int l = 0; l < 3; ++l) {
+            const int d = a.dil[l];
+            const int ctx = (K - 1) * d;
+            {   // restore the saved contexts in front of the tiles, then x -> snake -> s1 tile
+                for (int i = tid; i < ctx * PW; i += kThreads) {
+                    s1h[(CTX1 - ctx) * PW + i] = c1h[c1off * PW + i];
+                    s1l[(CTX1 - ctx) * PW + i] = c1l[c1off * PW + i];
+                }
+                for (int i = tid; i < CTX2 * PW; i += kThreads) {
+                    s2h[i] = c2h[l * CTX2 * PW + i];
+                    s2l[i] = c2l[l * CTX2 * PW + i];
+                }
+                const float* ea = a.ea[2 * l];
+                const float* ieb = a.ieb[2 * l];
+                constexpr int CP = C / 2;
+                for (int i = tid; i < TT * CP; i += kThreads) {
+                    const int row = i / CP, cp = i % CP;
+                    const float2 v = *reinterpret_cast<const float2*>(cur + row * PF + 2 * cp);
+                    const float y0 = snake(v.x, __ldg(ea + 2 * cp), __ldg(ieb + 2 * cp));
+                    const float y1 = snake(v.y, __ldg(ea + 2 * cp + 1), __ldg(ieb + 2 * cp + 1));
+                    uint32_t hi, lw;
+                    split_pair(y0, y1, hi, lw);
+                    s1h[(CTX1 + row) * PW + cp] = hi;
+                    s1l[(CTX1 + row) * PW + cp] = lw;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < ctx * PW; i += kThreads) {      // history for the next tile
+                c1h[c1off * PW + i] = s1h[(CTX1 + TT - ctx) * PW + i];
+                c1l[c1off * PW + i] = s1l[(CTX1 + TT - ctx) * PW + i];
+            }
+            {
+                const float* ea = a.ea[2 * l + 1];
+                const float* ieb = a.ieb[2 * l + 1];
+                const float* bias = a.b1[l];
+                for (int tile = warp; tile < tiles; tile += kThreads / 32) {
+                    mma_rows<C, C, K, MT>(s1h_a, s1l_a, CTX1, a.f1h[l], a.f1l[l], d, tile * RW,
+                                          [&](int row, int co, float v0, float v1) {
+                                              const float y0 = snake(v0 + __ldg(bias + co), __ldg(ea + co), __ldg(ieb + co));
+                                              const float y1 = snake(v1 + __ldg(bias + co + 1), __ldg(ea + co + 1), __ldg(ieb + co + 1));
+                                              uint32_t hi, lw;
+                                              split_pair(y0, y1, hi, lw);
+                                              s2h[(CTX2 + row) * PW + (co >> 1)] = hi;
+                                              s2l[(CTX2 + row) * PW + (co >> 1)] = lw;
+                                          });
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < CTX2 * PW; i += kThreads) {
+                c2h[l * CTX2 * PW + i] = s2h[TT * PW + i];
+                c2l[l * CTX2 * PW + i] = s2l[TT * PW + i];
+            }
+            {
+                const float* bias = a.b2[l];
+                for (int tile = warp; tile < tiles; tile += kThreads / 32) {
+                    mma_rows<C, C, K, MT>(s2h_a, s2l_a, CTX2, a.f2h[l], a.f2l[l], 1, tile * RW,
+                                          [&](int row, int co, float v0, float v1) {
+                                              float2* p = reinterpret_cast<float2*>(cur + row * PF + co);
+                                              float2 c = *p;
+                                              c.x += v0 + __ldg(bias + co);
+                                              c.y += v1 + __ldg(bias + co + 1);
+                                              *p = c;
+                                          });
+                }
+            }
+            __syncthreads();
+            c1off += ctx;
+        }
+
+        // ---- write the tile, channel-last, coalesced (warm-up tiles are not written) ----
+        if (t0 >= t_begin) {
+            constexpr int V = C / 4;
+            for (int i = tid; i < TT * V; i += kThreads) {
+                const int tt = i / V, c4 = i - tt * V;
+                const int tg = t0 + tt;
+                if (tg < t_end)
+                    *reinterpret_cast<float4*>(dst + (size_t)tg * C + c4 * 4) =
+                        *reinterpret_cast<const float4*>(cur + tt * PF + c4 * 4);
+            }
+        }
+        // the next tile's input load overwrites xh/xl = s1, which the last conv no longer reads; cur is rewritten
+        // only after the barrier that follows the input load
     }
 }
 
@@ -502,20 +574,41 @@ __global__ void __launch_bounds__(kThreads) post_kernel(PostArgs a) {
     }
 }
 
+// tile rows and m16 tiles per warp of the streaming tensor-core kernel, per channel count
+template <int C> struct StreamTile { static constexpr int TT = 128, MT = 1; };
+template <> struct StreamTile<16> { static constexpr int TT = 256, MT = 2; };
+template <> struct StreamTile<8> { static constexpr int TT = 512, MT = 2; };
+
 template <int C, int U, int K>
-int launch_stage(const StageArgs& a, int B, int precision, cudaStream_t stream) {
+int launch_stage(const StageArgs& a_in, int B, int precision, cudaStream_t stream) {
     constexpr int HALO = 12 * (K - 1);
-    dim3 grid((a.n_out + a.TT - 1) / a.TT, B);
+    StageArgs a = a_in;
     if (precision >= 1) {
-        const int W = a.TT + HALO;
-        const size_t smem = (size_t)W * (RowLayout<C>::PF * 4 + 4 * RowLayout<C>::PW * 4);
-        static bool attr_set = false;
-        if (!attr_set) {
-            BVC_CUDA(cudaFuncSetAttribute(stage_mma_kernel<C, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            attr_set = true;
+        constexpr int TT = StreamTile<C>::TT, MT = StreamTile<C>::MT;
+        a.TT = TT;
+        const size_t smem = StreamLayout<C, K>::words(TT) * 4;
+        static int ctas_per_sm = 0, sms = 0;
+        if (!ctas_per_sm) {
+            BVC_CUDA(cudaFuncSetAttribute(stage_stream_kernel<C, U, K, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+            int dev = 0;
+            BVC_CUDA(cudaGetDevice(&dev));
+            BVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            BVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, stage_stream_kernel<C, U, K, MT>, kThreads, smem));
+            if (ctas_per_sm < 1) { set_error("vocoder stage kernel does not fit on an SM"); ctas_per_sm = 0; return BVC_ERR_DEVICE; }
         }
-        stage_mma_kernel<C, U, K><<<grid, kThreads, smem, stream>>>(a);
+        // time ranges per utterance: enough CTAs for ~4 waves (tail effect), but ranges long enough that the
+        // warm-up of a range (12 (K-1) samples) stays small against its length
+        const int tiles_total = (a.n_out + TT - 1) / TT;
+        const int want = (4 * sms * ctas_per_sm + B - 1) / B;
+        const int max_ranges = tiles_total / (4 * ((HALO + TT - 1) / TT)) > 0 ? tiles_total / (4 * ((HALO + TT - 1) / TT)) : 1;
+        int ranges = want < max_ranges ? want : max_ranges;
+        if (ranges < 1) ranges = 1;
+        const int tiles_per = (tiles_total + ranges - 1) / ranges;
+        ranges = (tiles_total + tiles_per - 1) / tiles_per;
+        dim3 grid(ranges, B);
+        stage_stream_kernel<C, U, K, MT><<<grid, kThreads, smem, stream>>>(a);
     } else {
+        dim3 grid((a.n_out + a.TT - 1) / a.TT, B);
         const int WP = a.TT + HALO + 4;
         const size_t smem = (size_t)3 * C * WP * sizeof(float);
         static bool attr_set = false;
