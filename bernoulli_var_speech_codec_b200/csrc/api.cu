@@ -29,7 +29,7 @@ struct bvc_handle {
     bool have_bvrnn = false, have_voc = false, have_frontend = false;
     Workspace ws;
     int64_t launches = 0;
-    int precision = 0;
+    int precision = 1;   // 1: split-bf16 tensor-core kernels (default, the measured path); 0: fp32 FFMA kernels
     std::vector<void*> allocs;
     cudaStream_t stream = nullptr;
     cudaEvent_t ws_event = nullptr;   // end of the last job that used the workspace (any stream)

@@ -35,6 +35,16 @@ __device__ __forceinline__ float snake(float x, float ea, float inv_eb) {
     const float s = sinf(x * ea);
     return x + inv_eb * (s * s);
 }
+// tensor-core path: two-constant Cody-Waite reduction to [-pi, pi] followed by MUFU.SIN (abs error ~4e-7 for the
+// argument range of the vocoder, |x e^alpha| << 1e4); the fp32 path keeps sinf
+__device__ __forceinline__ float snake_fast(float x, float ea, float inv_eb) {
+    const float y = x * ea;
+    const float k = rintf(y * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, y);
+    r = fmaf(k, 1.7484555e-7f, r);
+    const float s = __sinf(r);
+    return x + inv_eb * (s * s);
+}
 
 __global__ void pad_mel_kernel(const float* __restrict__ mel, float* __restrict__ out, int B, int T, int X) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,7 +277,7 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
 // One warp computes a (16 MT)-row x COUT tile of  out[r][co] = sum_{tap,ci} in[r + lead - (NTAPS-1-tap) d][ci] W[tap][ci][co]
 // for r = r0 .. r0 + 16 MT - 1.  inh/inl: shared-memory byte addresses of the split-bf16 activation rows (pitch
 // RowLayout<CIN>::PW words); `lead` = index of the buffer row that holds output row 0's undelayed input.
-// wh/wl: fragment-packed weights.  epi(r, co, v0, v1) receives channels (co, co+1) of output row r.
+// wh/wl: fragment-packed weights.  epi(r, nt, co, v0, v1) receives channels (co, co+1) = (8 nt + 2 q, +1) of output row r.
 template <int CIN, int COUT, int NTAPS, int MT, typename Epi>
 __device__ __forceinline__ void mma_rows(uint32_t inh, uint32_t inl, int lead, const uint2* __restrict__ wh,
                                          const uint2* __restrict__ wl, int d, int r0, Epi epi) {
@@ -333,8 +343,8 @@ __device__ __forceinline__ void mma_rows(uint32_t inh, uint32_t inl, int lead, c
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const int row = r0 + mt * 16 + g, co = nt * 8 + 2 * q;
-            epi(row, co, acc[mt][nt][0], acc[mt][nt][1]);
-            epi(row + 8, co, acc[mt][nt][2], acc[mt][nt][3]);
+            epi(row, nt, co, acc[mt][nt][0], acc[mt][nt][1]);
+            epi(row + 8, nt, co, acc[mt][nt][2], acc[mt][nt][3]);
         }
 }
 
@@ -425,14 +435,16 @@ __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
             const int tiles = (rows + RW - 1) / RW;
             const uint32_t xh_a = (uint32_t)__cvta_generic_to_shared(xh), xl_a = (uint32_t)__cvta_generic_to_shared(xl);
             constexpr int KC_UP = (2 * CIN) / 16, NT = C / 8;
+            float2 bup[NT];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bup[nt] = __ldg(reinterpret_cast<const float2*>(a.b_up + nt * 8 + 2 * (tid & 3)));
             for (int item = warp; item < U * tiles; item += kThreads / 32) {
                 const int r = item / tiles, tile = item - r * tiles;
                 const uint2* wh = a.upf_h + (size_t)r * KC_UP * NT * 32;
                 const uint2* wl = a.upf_l + (size_t)r * KC_UP * NT * 32;
-                mma_rows<CIN, C, 2, MT>(xh_a, xl_a, 1, wh, wl, 1, tile * RW, [&](int row, int co, float v0, float v1) {
+                mma_rows<CIN, C, 2, MT>(xh_a, xl_a, 1, wh, wl, 1, tile * RW, [&](int row, int nt, int co, float v0, float v1) {
                     if (row < rows)
-                        *reinterpret_cast<float2*>(cur + (U * row + r) * PF + co) =
-                            make_float2(v0 + __ldg(a.b_up + co), v1 + __ldg(a.b_up + co + 1));
+                        *reinterpret_cast<float2*>(cur + (U * row + r) * PF + co) = make_float2(v0 + bup[nt].x, v1 + bup[nt].y);
                 });
             }
         }
@@ -456,16 +468,14 @@ __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
                     s2h[i] = c2h[l * CTX2 * PW + i];
                     s2l[i] = c2l[l * CTX2 * PW + i];
                 }
-                const float* ea = a.ea[2 * l];
-                const float* ieb = a.ieb[2 * l];
-                constexpr int CP = C / 2;
-                for (int i = tid; i < TT * CP; i += kThreads) {
-                    const int row = i / CP, cp = i % CP;
+                constexpr int CP = C / 2;                       // kThreads % CP == 0: a thread keeps its channel pair
+                const int cp = tid % CP;
+                const float2 ea = __ldg(reinterpret_cast<const float2*>(a.ea[2 * l] + 2 * cp));
+                const float2 ieb = __ldg(reinterpret_cast<const float2*>(a.ieb[2 * l] + 2 * cp));
+                for (int row = tid / CP; row < TT; row += kThreads / CP) {
                     const float2 v = *reinterpret_cast<const float2*>(cur + row * PF + 2 * cp);
-                    const float y0 = snake(v.x, __ldg(ea + 2 * cp), __ldg(ieb + 2 * cp));
-                    const float y1 = snake(v.y, __ldg(ea + 2 * cp + 1), __ldg(ieb + 2 * cp + 1));
                     uint32_t hi, lw;
-                    split_pair(y0, y1, hi, lw);
+                    split_pair(snake_fast(v.x, ea.x, ieb.x), snake_fast(v.y, ea.y, ieb.y), hi, lw);
                     s1h[(CTX1 + row) * PW + cp] = hi;
                     s1l[(CTX1 + row) * PW + cp] = lw;
                 }
@@ -476,16 +486,21 @@ __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
                 c1l[c1off * PW + i] = s1l[(CTX1 + TT - ctx) * PW + i];
             }
             {
-                const float* ea = a.ea[2 * l + 1];
-                const float* ieb = a.ieb[2 * l + 1];
-                const float* bias = a.b1[l];
+                constexpr int NT = C / 8;
+                float2 bv[NT], ea[NT], ieb[NT];                 // per-thread constants: channels 8 nt + 2 q, +1
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int co = nt * 8 + 2 * (tid & 3);
+                    bv[nt] = __ldg(reinterpret_cast<const float2*>(a.b1[l] + co));
+                    ea[nt] = __ldg(reinterpret_cast<const float2*>(a.ea[2 * l + 1] + co));
+                    ieb[nt] = __ldg(reinterpret_cast<const float2*>(a.ieb[2 * l + 1] + co));
+                }
                 for (int tile = warp; tile < tiles; tile += kThreads / 32) {
                     mma_rows<C, C, K, MT>(s1h_a, s1l_a, CTX1, a.f1h[l], a.f1l[l], d, tile * RW,
-                                          [&](int row, int co, float v0, float v1) {
-                                              const float y0 = snake(v0 + __ldg(bias + co), __ldg(ea + co), __ldg(ieb + co));
-                                              const float y1 = snake(v1 + __ldg(bias + co + 1), __ldg(ea + co + 1), __ldg(ieb + co + 1));
+                                          [&](int row, int nt, int co, float v0, float v1) {
                                               uint32_t hi, lw;
-                                              split_pair(y0, y1, hi, lw);
+                                              split_pair(snake_fast(v0 + bv[nt].x, ea[nt].x, ieb[nt].x),
+                                                         snake_fast(v1 + bv[nt].y, ea[nt].y, ieb[nt].y), hi, lw);
                                               s2h[(CTX2 + row) * PW + (co >> 1)] = hi;
                                               s2l[(CTX2 + row) * PW + (co >> 1)] = lw;
                                           });
@@ -497,14 +512,17 @@ __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
                 c2l[l * CTX2 * PW + i] = s2l[TT * PW + i];
             }
             {
-                const float* bias = a.b2[l];
+                constexpr int NT = C / 8;
+                float2 bv[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) bv[nt] = __ldg(reinterpret_cast<const float2*>(a.b2[l] + nt * 8 + 2 * (tid & 3)));
                 for (int tile = warp; tile < tiles; tile += kThreads / 32) {
                     mma_rows<C, C, K, MT>(s2h_a, s2l_a, CTX2, a.f2h[l], a.f2l[l], 1, tile * RW,
-                                          [&](int row, int co, float v0, float v1) {
+                                          [&](int row, int nt, int co, float v0, float v1) {
                                               float2* p = reinterpret_cast<float2*>(cur + row * PF + co);
                                               float2 c = *p;
-                                              c.x += v0 + __ldg(bias + co);
-                                              c.y += v1 + __ldg(bias + co + 1);
+                                              c.x += v0 + bv[nt].x;
+                                              c.y += v1 + bv[nt].y;
                                               *p = c;
                                           });
                 }

@@ -142,7 +142,8 @@ int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T
 size_t bvc_workspace_bytes(const bvc_handle* h);
 /* Kernels launched by this library since the handle was created (bench evidence). */
 int64_t bvc_kernel_launches(const bvc_handle* h);
-/* Arithmetic mode of the GEMM/conv inner products: 0 = fp32 FFMA, 1 = split-bf16 tensor core. */
+/* Arithmetic mode of the GEMM/conv inner products: 1 = split-bf16 tensor core (default; the benchmarked path),
+ * 0 = fp32 FFMA kernels (slow cross-check path with reference-grade rounding). */
 int bvc_set_precision(bvc_handle* h, int32_t mode);
 
 /* Debug/parity taps: copy an internal device buffer of the LAST call to host.

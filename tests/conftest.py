@@ -42,16 +42,27 @@ def oracle_fix(ckpts, cfg_fix):
     return OracleCodec(cfg_fix, *ckpts)
 
 
-@pytest.fixture(scope="session")
-def model_var(ckpts, cfg_var):
-    from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
-    return BVRNNCodecModel(cfg_var, *ckpts).eval()
+# Every GPU parity test runs in both arithmetic modes of the library: 1 = split-bf16 tensor-core kernels (the
+# default and the path bench.py measures), 0 = fp32 FFMA kernels.
+PRECISIONS = [pytest.param(1, id="tensorcore"), pytest.param(0, id="fp32")]
 
 
-@pytest.fixture(scope="session")
-def model_fix(ckpts, cfg_fix):
+@pytest.fixture(scope="session", params=PRECISIONS)
+def model_var(request, ckpts, cfg_var):
     from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
-    return BVRNNCodecModel(cfg_fix, *ckpts).eval()
+    m = BVRNNCodecModel(cfg_var, *ckpts).eval()
+    m._engine.set_precision(request.param)
+    m.precision = request.param
+    return m
+
+
+@pytest.fixture(scope="session", params=PRECISIONS)
+def model_fix(request, ckpts, cfg_fix):
+    from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
+    m = BVRNNCodecModel(cfg_fix, *ckpts).eval()
+    m._engine.set_precision(request.param)
+    m.precision = request.param
+    return m
 
 
 def golden(name):
