@@ -494,11 +494,19 @@ int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
             rw.b_ih_q = up(bih_q);
             std::vector<float> zq = slice(d0, 0, H, 0, H);
             append(zq, ihz_q);
-            ok = ok && make_linear(h, zq, 4 * Hi, Hi, &rw.zcat_q);
+            W(zq, 4 * Hi, Hi, 256, &rw.g_zcat);
             std::vector<float> bq = to_vec(m["dec.0.bias"]);
             append(bq, bih_q);
             rw.b_zcat_q = up(bq);
         }
+        // hoisted layers over all B*T frames
+        W(to_vec(m["phi_x.0.weight"]), Hi, Xi, 256, &rw.g_px0);
+        W(to_vec(m["phi_x.2.weight"]), Hi, Hi, 256, &rw.g_px2);
+        W(to_vec(m["phi_x.4.weight"]), Hi, Hi, 256, &rw.g_px4);
+        W(slice(e0, 0, H, 0, H), Hi, Hi, 256, &rw.g_e0x);
+        W(to_vec(m["phi_z.0.weight"]), Hi, Zi, 256, &rw.g_pz0);
+        W(to_vec(m["phi_z.2.weight"]), Hi, Hi, 256, &rw.g_pz2);
+        W(to_vec(m["phi_z.4.weight"]), Hi, Hi, 256, &rw.g_pz4);
         void* p1 = nullptr; void* p2 = nullptr; void* p3 = nullptr;
         ok = ok && cudaMalloc(&p1, rec::SYNC_WORDS * sizeof(unsigned)) == cudaSuccess &&
              cudaMalloc(&p2, sizeof(rec::Program)) == cudaSuccess && cudaMallocHost(&p3, sizeof(rec::Program)) == cudaSuccess;

@@ -110,9 +110,10 @@ size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T) {
     const size_t BT = (size_t)B * T, H = w.H;
     const size_t Bp = ((size_t)B + 127) / 128 * 128;   // activation images cover whole 128-row m-tiles
     size_t n = 0;
-    n += BT * w.X + 64;                 // normalised mel
-    n += 2 * (BT * H + 64);             // two hoisted activation buffers
-    n += BT * 4 * H + 64;               // decode: hoisted [dec.0_z ; W_ih_z] . phi_z
+    const size_t BTp = (BT + 127) / 128 * 128;
+    n += BTp * 128 + BT * w.X + 64;     // input images (normalised mel padded to K = 128, or codes) / fp32 path: normalised mel
+    n += 2 * (BTp * H + 64);            // two hoisted activation buffers (images: hi + lo bf16 = 4 bytes per element)
+    n += BT * 4 * H + 64;               // hoisted fp32 output: encode [B*T, H], decode [dec.0_z ; W_ih_z] . phi_z [B*T, 4H]
     n += Bp * (40 * H + 2 * w.X + 2 * w.Z + 256) + 64 * 64;
     return n;
 }
@@ -419,9 +420,10 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     int G = 0;
     BVC_TRY(cluster_count(&G));
 
-    float* yn = ws.take(BT * X);
-    float* PA = ws.take(BT * H);
-    float* PB = ws.take(BT * H);
+    unsigned char* ynI = take_img(ws, (int)BT, 128);
+    unsigned char* PAi = take_img(ws, (int)BT, H);
+    unsigned char* PBi = take_img(ws, (int)BT, H);
+    float* E0x = ws.take(BT * H);
     float* hf = ws.take((size_t)B * H);
     float* dh = ws.take((size_t)B * H);
     float* gh = ws.take((size_t)B * 3 * H);
@@ -434,17 +436,12 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     unsigned char *d3I = take_img(ws, B, H), *x1I = take_img(ws, B, H), *x2I = take_img(ws, B, H);
     unsigned char* pxI = take_img(ws, B, H);
 
-    // hoisted over all frames (large GEMMs): phi_x(yn), then enc.0[:, :H] . phi_x
-    {
-        const size_t n = BT * X;
-        normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mel, w.mean, w.std, yn, n, X);
-        BVC_CHECK_LAUNCH();
-    }
-    BVC_TRY(run_linear(yn, X, (int)BT, w.px0, w.b_px0, H, PA, H, 1, s));
-    BVC_TRY(run_linear(PA, H, (int)BT, w.px2, w.b_px2, H, PB, H, 1, s));
-    BVC_TRY(run_linear(PB, H, (int)BT, w.px4, w.b_px4, H, PA, H, 1, s));
-    BVC_TRY(run_linear(PA, H, (int)BT, w.e0x, nullptr, 0, PB, H, 1, s));
-    float* E0x = PB;
+    // hoisted over all frames (tcgen05 GEMMs, gemm_umma.cu): yn = (y - mean) / std -> phi_x -> enc.0[:, :H] . phi_x
+    BVC_TRY(to_image(mel, (int)BT, X, w.mean, w.std, ynI, 2, s));
+    BVC_TRY(linear_umma(ynI, (int)BT, rw.g_px0, w.b_px0, 1, nullptr, 0, PAi, s));
+    BVC_TRY(linear_umma(PAi, (int)BT, rw.g_px2, w.b_px2, 1, nullptr, 0, PBi, s));
+    BVC_TRY(linear_umma(PBi, (int)BT, rw.g_px4, w.b_px4, 1, nullptr, 0, PAi, s));
+    BVC_TRY(linear_umma(PAi, (int)BT, rw.g_e0x, nullptr, 0, E0x, H, nullptr, s));
     BVC_TRY(rec::init_state(h0, hf, hI, B, H, s));
 
     rec::Program* p = rw.prog_host;
@@ -518,8 +515,9 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     int G = 0;
     BVC_TRY(cluster_count(&G));
 
-    float* PA = ws.take(BT * H);
-    float* PB = ws.take(BT * H);
+    unsigned char* zI_all = take_img(ws, (int)BT, Z);
+    unsigned char* PAi = take_img(ws, (int)BT, H);
+    unsigned char* PBi = take_img(ws, (int)BT, H);
     float* DZ = ws.take(BT * 4 * H);
     float* hf = ws.take((size_t)B * H);
     float* gh = ws.take((size_t)B * 3 * H);
@@ -528,11 +526,12 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     unsigned char *d3I = take_img(ws, B, H), *x1I = take_img(ws, B, H), *x2I = take_img(ws, B, H);
     unsigned char* pxI = take_img(ws, B, H);
 
-    // hoisted over all frames: phi_z(z), then [dec.0_z ; W_ih_z (gate-interleaved)] . phi_z + [b_d0 ; b_ih]
-    BVC_TRY(run_linear(codes, Z, (int)BT, w.pz0, w.b_pz0, H, PA, H, 1, s));
-    BVC_TRY(run_linear(PA, H, (int)BT, w.pz2, w.b_pz2, H, PB, H, 1, s));
-    BVC_TRY(run_linear(PB, H, (int)BT, w.pz4, w.b_pz4, H, PA, H, 1, s));
-    BVC_TRY(run_linear(PA, H, (int)BT, rw.zcat_q, rw.b_zcat_q, 0, DZ, 4 * H, 1, s));
+    // hoisted over all frames (tcgen05 GEMMs): phi_z(z), then [dec.0_z ; W_ih_z (gate-interleaved)] . phi_z + [b_d0 ; b_ih]
+    BVC_TRY(to_image(codes, (int)BT, Z, nullptr, nullptr, zI_all, Z / rec::CHUNK_K, s));
+    BVC_TRY(linear_umma(zI_all, (int)BT, rw.g_pz0, w.b_pz0, 1, nullptr, 0, PAi, s));
+    BVC_TRY(linear_umma(PAi, (int)BT, rw.g_pz2, w.b_pz2, 1, nullptr, 0, PBi, s));
+    BVC_TRY(linear_umma(PBi, (int)BT, rw.g_pz4, w.b_pz4, 1, nullptr, 0, PAi, s));
+    BVC_TRY(linear_umma(PAi, (int)BT, rw.g_zcat, rw.b_zcat_q, 0, DZ, 4 * H, nullptr, s));
     BVC_TRY(rec::init_state(h0, hf, hI, B, H, s));
 
     rec::Program* p = rw.prog_host;

@@ -63,6 +63,13 @@ struct LinearWeights {
 int linear_forward(const float* A, int lda, int M, const LinearWeights& W, const LinearEpilogue& ep,
                    int precision, cudaStream_t stream);
 
+// tcgen05 path for the hoisted layers (gemm_umma.cu): operands are shared-memory images (recurrent.cuh)
+struct WImg;
+int to_image(const float* x, int M, int K_in, const float* mean, const float* sd, unsigned char* img, int kchunks,
+             cudaStream_t stream);
+int linear_umma(const unsigned char* a_img, int M, const WImg& w, const float* bias, int act, float* out_f, int ldo,
+                unsigned char* out_img, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------
 // log-mel front end (logmel.cu)
 // ---------------------------------------------------------------------------
@@ -97,7 +104,8 @@ struct RecurrentWeights {
     // reconstructed mel never has to exist on the recurrence's critical path (bvrnn.py:202-204)
     WImg e0h, d0h, whh_q, e2, e4, pz0, pz2, pz4, d0z, ihz_q, d2, d4, d6, x1f, px2, px4, ihx_q;
     float *b_e0 = nullptr, *b_hh_q = nullptr, *b_d0 = nullptr, *b_ih_q = nullptr, *b_x1f = nullptr, *b_d6p = nullptr;
-    LinearWeights zcat_q;            // [dec.0[:, :H]; W_ih[:, H:] gate-interleaved] for the hoisted decode GEMM
+    // hoisted layers (gemm_umma.cu), weight images with bn = 256; g_zcat = [dec.0[:, :H]; W_ih[:, H:] gate-interleaved]
+    WImg g_px0, g_px2, g_px4, g_e0x, g_pz0, g_pz2, g_pz4, g_zcat;
     float* b_zcat_q = nullptr;
     unsigned* sync_words = nullptr;  // device: abort flag + one barrier counter per m-tile
     rec::Program* prog_dev = nullptr;
