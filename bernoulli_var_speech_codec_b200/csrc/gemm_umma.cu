@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(GemmArgs a) {
             }
             if (a.act) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = elu1(v[i]);
+                for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
             }
             if (a.out_img && col0 < a.N) store_img16(a.out_img, m_tile, a.out_kchunks, row, col0, v);
             if (a.out_f) {

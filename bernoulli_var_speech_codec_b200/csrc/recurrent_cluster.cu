@@ -39,7 +39,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int A_SLOTS = 4;                                   // chunks of the resident activation quarter
-constexpr int W_SLOTS = 3;
+constexpr int W_SLOTS = 4;
 constexpr int W_SLOT_BYTES = 2 * 64 * 128;                   // bn <= 64
 constexpr int ACC_SLOTS = 8;
 constexpr int ACC_COLS = 64;
@@ -49,7 +49,7 @@ constexpr int STG_BUF_BYTES = (CLUSTER - 1) * STG_SENDER_BYTES;
 constexpr int SMEM_A = 0;
 constexpr int SMEM_W = SMEM_A + A_SLOTS * ACT_CHUNK_BYTES;
 constexpr int SMEM_STG = SMEM_W + W_SLOTS * W_SLOT_BYTES;
-constexpr int SMEM_TOTAL = SMEM_STG + 2 * STG_BUF_BYTES;     // 224 KiB
+constexpr int SMEM_TOTAL = SMEM_STG + STG_BUF_BYTES;         // 216 KiB
 constexpr int SMEM_DYNAMIC = SMEM_TOTAL + 3072;              // control block (3 KiB) in front; the whole 227 KiB of the SM
 
 struct Bars {
@@ -59,8 +59,8 @@ struct Bars {
     uint64_t accFull[ACC_SLOTS];   // accumulator complete (tcgen05.commit)
     uint64_t accEmpty[ACC_SLOTS];  // accumulator drained (4 epilogue warps)
     uint64_t aFree;                // all MMAs of the job retired: activation buffer reusable
-    uint64_t stgFull[2];           // the 3 peers' partials have landed in my staging buffer (expect_tx / st.async complete_tx)
-    uint64_t stgEmpty[2];          // the 3 peers finished reading their staging buffer
+    uint64_t stgFull;              // the 3 peers' partials have landed in my staging buffer (expect_tx / st.async complete_tx)
+    uint64_t stgEmpty;             // the 3 peers finished reading their staging buffer
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -311,7 +311,7 @@ __device__ __forceinline__ void finalize16(const Op& op, const Frame& fr, int t,
     }
     if (op.act) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = elu1(v[i]);
+        for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
     }
     if (op.kind == KIND_MEL) {
         if (fr.mel_out) {
@@ -464,7 +464,8 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
         for (int i = 0; i < W_SLOTS; ++i) { mbar_init(&bars.fullW[i], 1); mbar_init(&bars.emptyW[i], 1); }
         for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&bars.accFull[i], 1); mbar_init(&bars.accEmpty[i], 4); }
         mbar_init(&bars.aFree, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars.stgFull[i], 1); mbar_init(&bars.stgEmpty[i], 4 * (CLUSTER - 1)); }
+        mbar_init(&bars.stgFull, 1);
+        mbar_init(&bars.stgEmpty, 4 * (CLUSTER - 1));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         if ((smem_u32(smem_dyn) & 1023u) != 0) atomicCAS(abort_flag, 0, 90);   // SWIZZLE_128B operands need 1 KiB alignment
         // this CTA's schedule
@@ -645,25 +646,27 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     const uint32_t taddr = t_lane + slot * ACC_COLS;
                     float v[16];
                     if (pl.split) {
-                        const int buf = sIt & 1, sr = sIt >> 1;
+                        // One staging buffer: the epilogue handles one tile at a time anyway, and the peers run the same
+                        // schedule, so "all peers have read tile s - 1" is already true when tile s is ready to be sent.
+                        const int sr = sIt;
                         ++sIt;
                         float acc[64], own[16];
                         tmem_ld64(taddr, acc);
                         tc_fence_before();
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(10);
-                        // my staging slot at every peer is free once all peers have read their copy of two tiles ago
-                        if (sr >= 1 && !mbar_wait<false>(&bars.stgEmpty[buf], (sr - 1) & 1, abort_flag, 32)) { dead = true; break; }
-                        const uint32_t stg_send = smem_base + SMEM_STG + buf * STG_BUF_BYTES;
-                        const unsigned char* stg_recv = smem_gen + SMEM_STG + buf * STG_BUF_BYTES;
+                        // my staging slot at every peer is free once all peers have read the previous tile
+                        if (sr >= 1 && !mbar_wait<false>(&bars.stgEmpty, (sr - 1) & 1, abort_flag, 32)) { dead = true; break; }
+                        const uint32_t stg_send = smem_base + SMEM_STG;
+                        const unsigned char* stg_recv = smem_gen + SMEM_STG;
                         // arm my own staging barrier for the 3 x 128 x qc floats the peers will store (st.async complete_tx)
-                        if (tid == 128) mbar_expect_tx(&bars.stgFull[buf], (uint32_t)((CLUSTER - 1) * TILE_M * qc * 4));
-                        if (qc == 16) exchange<16>(acc, rank, row, stg_send, smem_u32(&bars.stgFull[buf]), own);
-                        else exchange<12>(acc, rank, row, stg_send, smem_u32(&bars.stgFull[buf]), own);
+                        if (tid == 128) mbar_expect_tx(&bars.stgFull, (uint32_t)((CLUSTER - 1) * TILE_M * qc * 4));
+                        if (qc == 16) exchange<16>(acc, rank, row, stg_send, smem_u32(&bars.stgFull), own);
+                        else exchange<12>(acc, rank, row, stg_send, smem_u32(&bars.stgFull), own);
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(0);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(11);
-                        if (!mbar_wait<false>(&bars.stgFull[buf], sr & 1, abort_flag, 33)) { dead = true; break; }
+                        if (!mbar_wait<false>(&bars.stgFull, sr & 1, abort_flag, 33)) { dead = true; break; }
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(14);
                         if (qc == 16) reduce_parts<16>(own, rank, row, stg_recv, v);
                         else reduce_parts<12>(own, rank, row, stg_recv, v);
@@ -672,7 +675,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         if (lane == 0) {
 #pragma unroll
                             for (int p = 0; p < CLUSTER; ++p)
-                                if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty[buf]), (uint32_t)p));
+                                if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)p));
                         }
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(1);
                     } else {
