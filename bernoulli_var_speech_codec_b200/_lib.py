@@ -47,6 +47,8 @@ SYMBOLS = {
     "bvc_vocoder_out_len": (C.c_int64, [_P, _I]),
     "bvc_encode_host": (C.c_int, [_P, _P, _I, _I, _F, _F, _P]),
     "bvc_decode_host": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),
+    "bvc_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "bvc_host_free": (C.c_int, [_P]),
     "bvc_workspace_bytes": (C.c_size_t, [_P]),
     "bvc_kernel_launches": (C.c_int64, [_P]),
     "bvc_set_precision": (C.c_int, [_P, _I]),

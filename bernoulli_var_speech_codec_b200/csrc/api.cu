@@ -824,6 +824,22 @@ int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T
     return BVC_OK;
 }
 
+int bvc_host_alloc(void** out, size_t bytes) {
+    REQUIRE(out && bytes > 0, BVC_ERR_INVALID, "bvc_host_alloc: bad argument");
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostAlloc of " + std::to_string(bytes >> 20) + " MiB failed");
+        return BVC_ERR_NOMEM;
+    }
+    *out = p;
+    return BVC_OK;
+}
+int bvc_host_free(void* p) {
+    if (p) BVC_CUDA(cudaFreeHost(p));
+    return BVC_OK;
+}
+
 size_t bvc_workspace_bytes(const bvc_handle* h) { return h ? h->ws.bytes : 0; }
 int64_t bvc_kernel_launches(const bvc_handle* h) { return h ? h->launches : 0; }
 

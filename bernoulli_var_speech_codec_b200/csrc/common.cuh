@@ -203,5 +203,8 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v);
 // recurrence's critical path: 16 serial evaluations per epilogue thread)
 __device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+// tanh(v) = 1 - 2 / (1 + e^{2v}); saturates correctly: e^{2v} -> inf gives 1, -> 0 gives -1
+__device__ __forceinline__ float tanh_fast(float v) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * v)); }
 
 }  // namespace bvc

@@ -151,6 +151,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -336,9 +345,10 @@ __device__ __forceinline__ void finalize_gru(const Frame& fr, int t, int m, int 
     float hn[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float rr = sigmoidf_(v[e] + pf.a[e] + pf.b[e]);
-        const float zg = sigmoidf_(v[4 + e] + pf.a[4 + e] + pf.b[4 + e]);
-        const float nn = tanhf(v[8 + e] + pf.a[8 + e] + rr * pf.b[8 + e]);
+        // ex2-based sigmoid / tanh (abs error ~2e-7): the precise versions cost ~1.5 us per GRU tile on the critical path
+        const float rr = sigmoid_fast(v[e] + pf.a[e] + pf.b[e]);
+        const float zg = sigmoid_fast(v[4 + e] + pf.a[4 + e] + pf.b[4 + e]);
+        const float nn = tanh_fast(v[8 + e] + pf.a[8 + e] + rr * pf.b[8 + e]);
         hn[e] = (pf.b[12 + e] - nn) * zg + nn;
     }
     uint32_t h0, l0, h1, l1;
@@ -509,93 +519,99 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     if (bad_setup) {
         // fall through to the common exit
     } else if (warp == 1) {
-        // =========================== copy thread ===========================
-        if (lane == 0) {
-            uint32_t wIt = 0, aIt = 0;
-            bool dead = false;
-            for (int t = 0; t < T && !dead; ++t) {
-                for (int ph = 0; ph < n_phases && !dead; ++ph) {
-                    const PhaseLocal& pl = ctl.ph[ph];
-                    const int nck = pl.nck;
-                    const int nW = pl.n * nck;
-                    auto issue_w = [&](int i) {
-                        const int j = i / nck, c = i - j * nck;
-                        const uint32_t e = ctl.ent[pl.e_off + j];
-                        const Op& op = ctl.ops[e >> 8];
-                        const int nt = (int)(e & 0xFF);
-                        const int slot = wIt % W_SLOTS, round = wIt / W_SLOTS;
-                        if (round >= 1 && !mbar_wait<false>(&bars.emptyW[slot], (round - 1) & 1, abort_flag, 11)) { dead = true; return; }
-                        const uint32_t bytes = 2u * op.bn * 128u;
-                        const unsigned char* src = op.w_img + ((size_t)nt * pl.k_chunks + pl.kc0 + c) * bytes;
+        // =========================== copy warp ===========================
+        // The whole warp walks the schedule (uniform control flow); one elected lane issues the bulk copies.  Issuing
+        // from inside an `if (lane == 0)` region instead makes the compiler wrap every instruction that takes uniform
+        // registers (UBLKCP, UTCHMMA) in an elect/R2UR loop.
+        uint32_t wIt = 0, aIt = 0;
+        bool dead = false;
+        for (int t = 0; t < T && !dead; ++t) {
+            for (int ph = 0; ph < n_phases && !dead; ++ph) {
+                const PhaseLocal& pl = ctl.ph[ph];
+                const int nck = pl.nck;
+                const int nW = pl.n * nck;
+                auto issue_w = [&](int i) {
+                    const int j = i / nck, c = i - j * nck;
+                    const uint32_t e = ctl.ent[pl.e_off + j];
+                    const Op& op = ctl.ops[e >> 8];
+                    const int nt = (int)(e & 0xFF);
+                    const int slot = wIt % W_SLOTS, round = wIt / W_SLOTS;
+                    if (round >= 1 && !mbar_wait<false>(&bars.emptyW[slot], (round - 1) & 1, abort_flag, 11)) { dead = true; return; }
+                    const uint32_t bytes = 2u * op.bn * 128u;
+                    const unsigned char* src = op.w_img + ((size_t)nt * pl.k_chunks + pl.kc0 + c) * bytes;
+                    if (elect_one()) {
                         mbar_expect_tx(&bars.fullW[slot], bytes);
                         bulk_g2s(smem_base + SMEM_W + slot * W_SLOT_BYTES, src, bytes, &bars.fullW[slot]);
-                        ++wIt;
-                    };
-                    // weights do not depend on the previous phase: start them before waiting for it
-                    const int pre = nW < W_SLOTS ? nW : W_SLOTS;
-                    for (int i = 0; i < pre && !dead; ++i) issue_w(i);
-                    if (pl.n > 0 && !dead) {
-                        const unsigned char* src = pl.a_src;
-                        if (aIt >= 1 && !mbar_wait<false>(&bars.aFree, (aIt - 1) & 1, abort_flag, 12)) dead = true;
-                        const unsigned target = (unsigned)(t * n_phases + ph) * dom_ctas;
-                        if (ld_acquire(counter) < target) {
-                            const long long t0 = clock64();
-                            int spins = 0;
-                            while (ld_acquire(counter) < target) {
-                                if (((++spins) & 15) == 0) {
-                                    if (*(volatile int*)abort_flag) { dead = true; break; }
-                                    if (clock64() - t0 > 4000000000LL) { atomicCAS(abort_flag, 0, 1); dead = true; break; }
-                                }
+                    }
+                    __syncwarp();
+                    ++wIt;
+                };
+                // weights do not depend on the previous phase: start them before waiting for it
+                const int pre = nW < W_SLOTS ? nW : W_SLOTS;
+                for (int i = 0; i < pre && !dead; ++i) issue_w(i);
+                if (pl.n > 0 && !dead) {
+                    const unsigned char* src = pl.a_src;
+                    if (aIt >= 1 && !mbar_wait<false>(&bars.aFree, (aIt - 1) & 1, abort_flag, 12)) dead = true;
+                    const unsigned target = (unsigned)(t * n_phases + ph) * dom_ctas;
+                    if (ld_acquire(counter) < target) {
+                        const long long t0 = clock64();
+                        int spins = 0;
+                        while (ld_acquire(counter) < target) {
+                            if (((++spins) & 15) == 0) {
+                                if (*(volatile int*)abort_flag) { dead = true; break; }
+                                if (clock64() - t0 > 4000000000LL) { atomicCAS(abort_flag, 0, 1); dead = true; break; }
                             }
                         }
-                        BVC_TRACE(2);
-                        fence_proxy_async_all();   // the producers' generic-proxy stores -> this thread's async-proxy reads
-                        if (!dead) {
+                    }
+                    if (lane == 0) BVC_TRACE(2);
+                    if (!dead) {
+                        if (elect_one()) {
+                            fence_proxy_async_all();   // the producers' generic-proxy stores -> this thread's async-proxy reads
                             for (int c = 0; c < nck; ++c) {
                                 mbar_expect_tx(&bars.fullA[c], ACT_CHUNK_BYTES);
                                 bulk_g2s(smem_base + SMEM_A + c * ACT_CHUNK_BYTES, src + (size_t)c * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES,
                                          &bars.fullA[c]);
                             }
-                            ++aIt;
                         }
-                        BVC_TRACE(3);
+                        __syncwarp();
+                        ++aIt;
                     }
-                    for (int i = pre; i < nW && !dead; ++i) issue_w(i);
-                    BVC_TRACE(4);
+                    if (lane == 0) BVC_TRACE(3);
                 }
+                for (int i = pre; i < nW && !dead; ++i) issue_w(i);
+                if (lane == 0) BVC_TRACE(4);
             }
         }
-        __syncwarp();
     } else if (warp == 0) {
-        // =========================== MMA thread ===========================
-        if (lane == 0) {
-            uint32_t wIt = 0, accIt = 0;
-            uint32_t aUse[A_SLOTS] = {0, 0, 0, 0};
-            bool dead = false;
-            const uint64_t descA = make_desc(smem_base + SMEM_A), descW = make_desc(smem_base + SMEM_W);
-            for (int t = 0; t < T && !dead; ++t) {
-                for (int ph = 0; ph < n_phases && !dead; ++ph) {
-                    const PhaseLocal& pl = ctl.ph[ph];
-                    const int nck = pl.nck;
-                    for (int j = 0; j < pl.n && !dead; ++j) {
-                        const uint32_t e = ctl.ent[pl.e_off + j];
-                        const int bn = ctl.ops[e >> 8].bn;
-                        const int slot = accIt % ACC_SLOTS, round = accIt / ACC_SLOTS;
-                        if (round >= 1 && !mbar_wait<false>(&bars.accEmpty[slot], (round - 1) & 1, abort_flag, 21)) { dead = true; break; }
+        // =========================== MMA warp ===========================
+        uint32_t wIt = 0, accIt = 0;
+        uint32_t aUse[A_SLOTS] = {0, 0, 0, 0};
+        bool dead = false;
+        const uint64_t descA = make_desc(smem_base + SMEM_A), descW = make_desc(smem_base + SMEM_W);
+        for (int t = 0; t < T && !dead; ++t) {
+            for (int ph = 0; ph < n_phases && !dead; ++ph) {
+                const PhaseLocal& pl = ctl.ph[ph];
+                const int nck = pl.nck;
+                for (int j = 0; j < pl.n && !dead; ++j) {
+                    const uint32_t e = ctl.ent[pl.e_off + j];
+                    const int bn = ctl.ops[e >> 8].bn;
+                    const int slot = accIt % ACC_SLOTS, round = accIt / ACC_SLOTS;
+                    if (round >= 1 && !mbar_wait<false>(&bars.accEmpty[slot], (round - 1) & 1, abort_flag, 21)) { dead = true; break; }
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc(TILE_M, bn);
+                    const uint32_t d_tmem = tmem + slot * ACC_COLS;
+                    for (int c = 0; c < nck; ++c) {
+                        if (j == 0) {
+                            if (!mbar_wait<false>(&bars.fullA[c], aUse[c] & 1, abort_flag, 22)) { dead = true; break; }
+                            ++aUse[c];
+                            if (lane == 0 && c == 0) BVC_TRACE(5);
+                            if (lane == 0 && c == nck - 1) BVC_TRACE(6);
+                        }
+                        const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
+                        if (!mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
+                        ++wIt;
                         tc_fence_after();
-                        const uint32_t idesc = make_idesc(TILE_M, bn);
-                        const uint32_t d_tmem = tmem + slot * ACC_COLS;
-                        for (int c = 0; c < nck; ++c) {
-                            if (j == 0) {
-                                if (!mbar_wait<false>(&bars.fullA[c], aUse[c] & 1, abort_flag, 22)) { dead = true; break; }
-                                ++aUse[c];
-                                if (c == 0) BVC_TRACE(5);
-                                if (c == nck - 1) BVC_TRACE(6);
-                            }
-                            const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
-                            if (!mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
-                            ++wIt;
-                            tc_fence_after();
+                        if (elect_one()) {
                             const uint64_t dah = descA + (uint64_t)((c * ACT_CHUNK_BYTES) >> 4);
                             const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
                             const uint64_t dwh = descW + (uint64_t)((ws * W_SLOT_BYTES) >> 4);
@@ -607,16 +623,20 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                                 umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc, 1u);
                             }
                             umma_commit(&bars.emptyW[ws]);
+                            if (c == nck - 1) umma_commit(&bars.accFull[slot]);
                         }
-                        if (dead) break;
-                        umma_commit(&bars.accFull[slot]);
-                        ++accIt;
+                        __syncwarp();
                     }
-                    if (pl.n > 0 && !dead) { umma_commit(&bars.aFree); BVC_TRACE(7); }
+                    if (dead) break;
+                    ++accIt;
+                }
+                if (pl.n > 0 && !dead) {
+                    if (elect_one()) umma_commit(&bars.aFree);
+                    __syncwarp();
+                    if (lane == 0) BVC_TRACE(7);
                 }
             }
         }
-        __syncwarp();
     } else if (warp >= 4) {
         // =========================== epilogue warps ===========================
         const int quad = warp & 3;                     // TMEM lane quadrant this warp may access

@@ -138,6 +138,12 @@ int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, fl
 int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T, int32_t length,
                     float inv_scale_div, float* wav_host);
 
+/* Page-locked host memory for the host-buffer entry points above (cudaHostAlloc / cudaFreeHost).  Pinning a
+ * 226 MB result buffer costs ~37 ms, so a binding should pool these blocks instead of allocating per call
+ * (codec.py does: blocks return to its pool when the last tensor viewing them dies). */
+int bvc_host_alloc(void** out, size_t bytes);
+int bvc_host_free(void* p);
+
 /* Bytes of device workspace the handle holds for a (B, T) job (grown on demand). */
 size_t bvc_workspace_bytes(const bvc_handle* h);
 /* Kernels launched by this library since the handle was created (bench evidence). */
