@@ -24,3 +24,19 @@ t, codes_d = wall(lambda: m.encode(xd, 3000)); print("encode device: %.1f ms" % 
 t, codes_h = wall(lambda: m.encode(x, 3000)); print("encode host  : %.1f ms" % t)
 t, wav_d = wall(lambda: m.decode(codes_d, L)); print("decode device: %.1f ms" % t)
 t, wav_h = wall(lambda: m.decode(codes_h, L)); print("decode host  : %.1f ms" % t)
+# ---- the same work done by hand with torch copies, to locate hidden costs of the host-buffer entry points ----
+wav_pin = torch.empty(B, L, pin_memory=True)
+def manual_decode():
+    cd = codes_h.cuda(non_blocking=True)
+    wd = m.decode(cd, L)
+    wav_pin.copy_(wd, non_blocking=True)
+    torch.cuda.synchronize()
+    return wav_pin
+t, _ = wall(manual_decode); print("decode manual (H2D + device API + D2H): %.1f ms" % t)
+for i in range(4):
+    t0 = time.perf_counter(); w = m.decode(codes_h, L); t1 = time.perf_counter()
+    print("  decode host call %d: %.1f ms" % (i, (t1 - t0) * 1e3))
+    del w
+for i in range(3):
+    t0 = time.perf_counter(); w = m._engine.pinned.empty((B, L)); t1 = time.perf_counter()
+    print("  pool.empty %d: %.2f ms" % (i, (t1 - t0) * 1e3)); del w
