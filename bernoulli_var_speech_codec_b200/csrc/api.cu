@@ -643,6 +643,72 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
             for (int a = 0; a < 6; ++a) snake(rb + ".activations." + std::to_string(a), ch, &bw.act[a]);
         }
     }
+    // ---- tcgen05 stage kernel (vocoder.cu, stage_umma_kernel): weight stream in MMA issue order ----
+    for (int i = 0; i < w.n_stages; ++i) {
+        UmmaStageWeights& um = w.umma[i];
+        um.ready = false;
+        const int Cs = (int)(C0 >> (i + 1));
+        const bool cfg_ok = w.n_kernels == 3 && c.voc_res_kernels[0] == 3 && c.voc_res_kernels[1] == 7 && c.voc_res_kernels[2] == 11 &&
+                            c.voc_res_dilations[0] == 1 && c.voc_res_dilations[1] == 3 && c.voc_res_dilations[2] == 5;
+        if (!cfg_ok || Cs > 32 || Cs < 8) continue;
+        const int N = Cs < 16 ? 16 : Cs, SPC = 16384 / (N * 64);
+        std::vector<unsigned char> stream;
+        int n_jobs = 0, n_chunks = 0;
+        bool fits = true;
+        for (int l = 0; l < 3 && fits; ++l)
+            for (int conv2 = 0; conv2 < 2 && fits; ++conv2)
+                for (int cc = 0; cc < 3 && fits; ++cc) {
+                    const int j = 2 - cc;                       // chain 0 = k 11, 1 = k 7, 2 = k 3
+                    const int K = c.voc_res_kernels[j];
+                    const std::string rb = "resblocks." + std::to_string(i * 3 + j);
+                    const std::vector<float> f = folded(rb + (conv2 ? ".convs2." : ".convs1.") + std::to_string(l));   // [co, ci, tap]
+                    const int steps = Cs >= 16 ? K * Cs / 16 : (K + 1) / 2;
+                    UmmaJob& jb = um.jobs[n_jobs++];
+                    jb.chain = (short)cc; jb.layer = (short)l; jb.conv2 = (short)conv2; jb.K = (short)K;
+                    jb.d = (short)(conv2 ? 1 : c.voc_res_dilations[l]);
+                    jb.steps = (short)steps; jb.chunk0 = (short)n_chunks;
+                    for (int s0 = 0; s0 < steps; s0 += SPC) {
+                        if (n_chunks >= 48) { fits = false; break; }
+                        const int s1 = std::min(steps, s0 + SPC);
+                        um.chunk_off[n_chunks] = (int)stream.size();
+                        um.chunk_bytes[n_chunks] = (s1 - s0) * N * 64;
+                        ++n_chunks;
+                        for (int st = s0; st < s1; ++st) {
+                            std::vector<uint16_t> blk((size_t)N * 32, 0);   // [part][group][N][8]
+                            for (int gq = 0; gq < 2; ++gq)
+                                for (int n = 0; n < Cs; ++n)
+                                    for (int e = 0; e < 8; ++e) {
+                                        int tap, ci;
+                                        if (Cs >= 16) { const int spt = Cs / 16; tap = st / spt; ci = (st % spt) * 16 + gq * 8 + e; }
+                                        else { tap = 2 * st + gq; ci = e; }
+                                        const float v = tap < K ? f[((size_t)n * Cs + ci) * K + tap] : 0.f;
+                                        const uint16_t vh = f2bf(v), vl = f2bf(v - bf2f(vh));
+                                        blk[((size_t)(0 * 2 + gq) * N + n) * 8 + e] = vh;
+                                        blk[((size_t)(1 * 2 + gq) * N + n) * 8 + e] = vl;
+                                    }
+                            const unsigned char* bp = reinterpret_cast<const unsigned char*>(blk.data());
+                            stream.insert(stream.end(), bp, bp + blk.size() * 2);
+                        }
+                    }
+                    jb.nchunks = (short)(n_chunks - jb.chunk0);
+                }
+        if (!fits) continue;
+        um.n_chunks = n_chunks;
+        um.wstream = dev_upload(h, stream);
+        ok = ok && um.wstream;
+        for (int cc = 0; cc < 3; ++cc) {
+            const AmpBlockWeights& bw = w.blocks[i * 3 + (2 - cc)];
+            const std::string rb = "resblocks." + std::to_string(i * 3 + (2 - cc));
+            std::vector<float> acc((size_t)Cs, 0.f);
+            for (int l = 0; l < 3; ++l) {
+                um.b1[cc][l] = bw.b1[l];
+                const std::vector<float> b2 = to_vec(m[rb + ".convs2." + std::to_string(l) + ".bias"]);
+                for (int q = 0; q < Cs; ++q) acc[q] += b2[q];
+                um.bsum[cc][l] = up(acc);
+            }
+        }
+        um.ready = ok;
+    }
     snake("activation_post", ch, &w.act_post);
     w.w_post = up(folded("conv_post"));   // [1, ci, 7] is already [ci][tap]
     w.b_post = up(to_vec(m["conv_post.bias"]));

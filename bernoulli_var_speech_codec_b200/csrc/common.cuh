@@ -170,6 +170,21 @@ struct AmpBlockWeights {
     uint2 *f1h[3], *f1l[3], *f2h[3], *f2l[3];
     SnakeParams act[6];
 };
+// Stage on the 5th-gen tensor cores (vocoder.cu, stage_umma_kernel): one tile = 18 convolution "jobs" (3 resblocks x
+// 3 layers x 2 convs) whose weights are streamed in MMA issue order as chunks of <= 16 KiB
+struct UmmaJob {
+    short chain, layer, conv2, K, d, steps, chunk0, nchunks;
+};
+struct UmmaStageWeights {
+    bool ready = false;
+    const unsigned char* wstream = nullptr;   // all chunks of one tile, concatenated
+    int n_chunks = 0;
+    int chunk_off[48];
+    int chunk_bytes[48];
+    UmmaJob jobs[18];
+    const float* b1[3][3];                    // [chain][layer] bias of the dilated conv
+    const float* bsum[3][3];                  // [chain][layer] sum of the second convs' biases of layers 0..layer
+};
 struct VocoderWeights {
     int n_mels = 0, c0 = 0, n_stages = 0, n_kernels = 0;
     int rates[4], dil[3], rks[3];
@@ -179,6 +194,7 @@ struct VocoderWeights {
     float* b_up[4];
     uint2 *upf_h[4], *upf_l[4];   // per output phase r: 2-tap fragment-packed weights (taps r+U, r), phases concatenated
     AmpBlockWeights blocks[12];
+    UmmaStageWeights umma[4];
     SnakeParams act_post;
     float* w_post = nullptr;  // [ci][tap]
     float* b_post = nullptr;  // [1]

@@ -22,6 +22,8 @@
 //                bf16 (hi, lo) rows [time][C]; a tap is a row offset of the A fragment, so no im2col
 //                copy exists.  x.w ~= x_hi.w_hi + x_hi.w_lo + x_lo.w_hi.  The residual stream stays fp32.
 #include <cuda_bf16.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -547,7 +549,519 @@ __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
     }
 }
 
+// ===========================================================================
+// precision 1, C <= 32: stage kernel on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM)
+// ===========================================================================
+// One CTA owns (utterance, time range) and runs ALL THREE resblocks (k = 11, 7, 3) of the stage on tiles of 128
+// output samples, streaming over time like stage_stream_kernel (causal contexts carried in shared memory).
+//   implicit GEMM   M = 128 time rows, N = C_out (16 for C = 8, zero padded), K = taps x C_in in k16 steps.
+//                   Conv inputs live in shared memory as split-bf16 NO-SWIZZLE K-major operands laid out
+//                   [hi | lo][8-channel group][row][8 channels]: rows are 16 bytes apart, so a tap is nothing but a
+//                   shift of the descriptor's start address (LBO = group stride, SBO = 128 B).  For C = 8 one k16
+//                   step covers two taps: the second K group is the same buffer d rows later (LBO = 16 d).
+//   residual        the fp32 residual stream x of each resblock lives in TMEM; the second conv of a layer accumulates
+//                   straight onto it (x += conv2(...)); biases of the second convs are added when x is read
+//   roles           warp 0 issues the MMAs of the 18 jobs of a tile (3 resblocks x 3 layers x 2 convs) round-robin over
+//                   the resblocks; warp 1 streams the weights of the jobs in issue order (cp.async.bulk, 16 KiB
+//                   chunks, 3-slot ring); warps 4-7 are the epilogue (thread = time row): TMEM -> bias -> SnakeBeta ->
+//                   split bf16 -> next conv's operand buffer.  While the epilogue of one resblock runs, the tensor core
+//                   works on the other two.
+//   tile prologue   input tile (mean of the producer's partials) -> ConvTranspose1d with mma.sync (3 % of the MACs) ->
+//                   x of the three resblocks (tcgen05.st) and their first conv inputs
+constexpr int UM_TT = 128;
+constexpr int UM_PADR = 8;
+constexpr int UM_WSLOTS = 3;
+constexpr int UM_WSLOT_BYTES = 16384;
+__host__ __device__ constexpr int um_K(int c) { return c == 0 ? 11 : c == 1 ? 7 : 3; }
+__host__ __device__ constexpr int um_R1(int c) { return (um_K(c) - 1) * 5 + UM_TT + UM_PADR; }
+__host__ __device__ constexpr int um_R2(int c) { return (um_K(c) - 1) + UM_TT + UM_PADR; }
+
+template <int C, int U>
+struct UmLayout {
+    static constexpr int G = C / 8, N = C < 16 ? 16 : C, CIN = 2 * C;
+    static constexpr int PWI = RowLayout<CIN>::PW;
+    static constexpr int NJ = UM_TT / U + 1;
+    // byte offsets
+    __host__ __device__ static constexpr int a1(int c) { return c == 0 ? 0 : a1(c - 1) + 2 * G * um_R1(c - 1) * 16; }
+    __host__ __device__ static constexpr int a2(int c) { return c == 0 ? a1(3) : a2(c - 1) + 2 * G * um_R2(c - 1) * 16; }
+    // saved contexts: per chain [layer][part][group][row][16 B]; layer l of the dilated conv has (K-1) d_l rows
+    __host__ __device__ static constexpr int c1(int c) { return c == 0 ? a2(3) : c1(c - 1) + 2 * G * (um_K(c - 1) - 1) * 9 * 16; }
+    __host__ __device__ static constexpr int c2(int c) { return c == 0 ? c1(3) : c2(c - 1) + 2 * G * (um_K(c - 1) - 1) * 3 * 16; }
+    static constexpr int wring = (c2(3) + 1023) / 1024 * 1024;
+    static constexpr int x0 = wring + UM_WSLOTS * UM_WSLOT_BYTES;          // fp32 [128][C + 4]
+    static constexpr int xin = x0 + UM_TT * (C + 4) * 4;                   // hi, lo [NJ + 16][PWI] words
+    static constexpr int total = xin + 2 * (NJ + 16) * PWI * 4;
+    static constexpr int tmem_cols = 6 * N <= 128 ? 128 : 256;
+};
+
+struct UmmaStageArgs {
+    const float* in_p[3];
+    int n_parts;
+    long long in_bstride;
+    int n_in, n_out;
+    const float* b_up;
+    const uint2* upf_h;
+    const uint2* upf_l;
+    const float* ea[3][6];
+    const float* ieb[3][6];
+    float* out;                 // [B, n_out, C] channel-last: the mean of the three resblocks
+    unsigned long long* trace;  // bring-up: CTA (0,0), tile 2: per job 4 %globaltimer stamps (+ 2 for the tile prologue)
+    UmmaStageWeights w;
+};
+
+__device__ __forceinline__ uint32_t um_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool um_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded: a protocol bug traps (surfaces as a CUDA error at the next API call) instead of hanging the GPU
+__device__ __forceinline__ void um_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = um_smem_u32(bar);
+    if (um_try(b, parity)) return;
+    const long long t0 = clock64();
+    while (!um_try(b, parity)) {
+        if (clock64() - t0 > 4000000000LL) asm volatile("trap;\n");
+    }
+}
+__device__ __forceinline__ unsigned long long um_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(v));
+    return v;
+}
+#define UM_TRACE(slot)                                                                         \
+    do {                                                                                       \
+        if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && tile == 2) a.trace[slot] = um_ns(); \
+    } while (0)
+__device__ __forceinline__ void um_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(um_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool um_elect() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// no-swizzle K-major descriptor: LBO = byte stride between the two 8-wide K groups of a k16 step, SBO = 128 B (8 rows)
+__device__ __forceinline__ uint64_t um_desc(uint32_t addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void um_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void um_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(um_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void um_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void um_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void um_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void um_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+
+// 8 channels of one row -> 16 bytes of the hi part and of the lo part
+__device__ __forceinline__ void um_store8(unsigned char* part_hi, int part_stride, int offset16, const float* y) {
+    uint4 h, l;
+    split_pair(y[0], y[1], h.x, l.x); split_pair(y[2], y[3], h.y, l.y);
+    split_pair(y[4], y[5], h.z, l.z); split_pair(y[6], y[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(part_hi + (size_t)offset16 * 16) = h;
+    *reinterpret_cast<uint4*>(part_hi + part_stride + (size_t)offset16 * 16) = l;
+}
+
+template <int C, int U>
+__global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(UmmaStageArgs a) {
+    using L = UmLayout<C, U>;
+    constexpr int G = L::G, N = L::N, CIN = L::CIN, PWI = L::PWI, NJ = L::NJ, PX = C + 4;
+    constexpr int HALO = 12 * (11 - 1);
+    constexpr int UM_THREADS = 128 + 128 * G;     // warps 0-3: MMA issue, weight stream, 2 idle; then G epilogue groups of 4 warps
+    extern __shared__ __align__(1024) unsigned char um_smem[];
+    __shared__ __align__(8) uint64_t a_ready[3], d_ready[3], w_full[UM_WSLOTS], w_empty[UM_WSLOTS];
+    __shared__ uint32_t tmem_slot;
+    unsigned char* sm = um_smem;
+    const uint32_t sm_a = um_smem_u32(um_smem);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int tiles_total = (a.n_out + UM_TT - 1) / UM_TT;
+    const int tiles_per = (tiles_total + gridDim.x - 1) / gridDim.x;
+    const int t_begin = blockIdx.x * tiles_per * UM_TT;
+    const int t_end = min(a.n_out, t_begin + tiles_per * UM_TT);
+    if (t_begin >= t_end) return;
+    const int t_first = max(0, t_begin - ((HALO + UM_TT - 1) / UM_TT) * UM_TT);   // warm-up tiles (outputs discarded)
+    const int n_tiles = (t_end - t_first + UM_TT - 1) / UM_TT;
+
+    // zero everything once: causal zero history, and the pad rows that zero-weight taps may touch must be finite
+    for (int i = tid; i < L::wring / 16; i += UM_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&a_ready[i])), "r"(4 * G));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&d_ready[i])), "r"(1));
+        }
+        for (int i = 0; i < UM_WSLOTS; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&w_full[i])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&w_empty[i])), "r"(1));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(um_smem_u32(&tmem_slot)),
+                     "r"((uint32_t)L::tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 1) {
+        // =========================== weight stream ===========================
+        uint32_t it = 0;
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            for (int ch = 0; ch < a.w.n_chunks; ++ch, ++it) {
+                const int slot = it % UM_WSLOTS, round = it / UM_WSLOTS;
+                if (round >= 1) um_wait(&w_empty[slot], (round - 1) & 1);
+                if (um_elect()) {
+                    const uint32_t bytes = (uint32_t)a.w.chunk_bytes[ch];
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(um_smem_u32(&w_full[slot])), "r"(bytes)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                                     sm_a + L::wring + slot * UM_WSLOT_BYTES),
+                                 "l"(a.w.wstream + a.w.chunk_off[ch]), "r"(bytes), "r"(um_smem_u32(&w_full[slot]))
+                                 : "memory");
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 0) {
+        // =========================== MMA issue ===========================
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UM_TT >> 4) << 24);
+        constexpr int SPC = UM_WSLOT_BYTES / (N * 64);       // k16 steps per weight chunk
+        uint32_t wit = 0;
+        uint32_t jobs_done[3] = {0, 0, 0};                    // per chain: selects the parity of a_ready
+        for (int tile = 0; tile < n_tiles; ++tile) {
+#pragma unroll 1
+            for (int ji = 0; ji < 18; ++ji) {
+                const UmmaJob jb = a.w.jobs[ji];
+                const int c = jb.chain;
+                um_wait(&a_ready[c], jobs_done[c] & 1);
+                ++jobs_done[c];
+                if (lane == 0) UM_TRACE(ji * 4 + 0);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const int K = jb.K, d = jb.d;
+                const int R = jb.conv2 ? (K - 1) + UM_TT + UM_PADR : (K - 1) * 5 + UM_TT + UM_PADR;
+                const int lead = jb.conv2 ? (K - 1) : (K - 1) * 5;
+                const uint32_t abase = sm_a + (jb.conv2 ? (c == 0 ? L::a2(0) : c == 1 ? L::a2(1) : L::a2(2))
+                                                        : (c == 0 ? L::a1(0) : c == 1 ? L::a1(1) : L::a1(2)));
+                const uint32_t d_tmem = tmem + (uint32_t)(c * 2 * N + (jb.conv2 ? 0 : N));
+                // Descriptors advance by plain additions on their 16-byte-unit address field:
+                //   C >= 16: step (tap, channel pair gq): +d rows per tap, +2 R rows per channel pair (two 8-channel groups)
+                //   C == 8 : step s covers taps 2s, 2s+1: +2 d rows per step, LBO = d rows
+                constexpr int SPT = C >= 16 ? C / 16 : 1;
+                const uint64_t dA0 = um_desc(abase + (uint32_t)((lead - (K - 1) * d) * 16), C >= 16 ? (uint32_t)(R * 16) : (uint32_t)(d * 16));
+                const uint32_t a_lo16 = (uint32_t)(G * R);                       // lo part, in 16-byte units
+                const uint32_t step_tap16 = C >= 16 ? (uint32_t)d : (uint32_t)(2 * d);
+                uint32_t tap_off16 = 0, gq = 0;                                  // running position of the next step
+                uint32_t first = jb.conv2 ? 1u : 0u;                             // the second conv accumulates onto x in TMEM
+                for (int s0 = 0; s0 < jb.steps; s0 += SPC) {
+                    const int slot = wit % UM_WSLOTS, round = wit / UM_WSLOTS;
+                    um_wait(&w_full[slot], round & 1);
+                    ++wit;
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const int s1 = min(jb.steps, s0 + SPC);
+                    if (um_elect()) {
+                        uint64_t dwh = um_desc(sm_a + L::wring + slot * UM_WSLOT_BYTES, N * 16);
+#pragma unroll 2
+                        for (int s = s0; s < s1; ++s) {
+                            const uint64_t dah = dA0 + (uint64_t)(tap_off16 + gq * (uint32_t)(2 * R));
+                            const uint64_t dal = dah + a_lo16, dwl = dwh + (uint64_t)(N * 2);
+                            um_mma(d_tmem, dal, dwh, idesc, first);
+                            um_mma(d_tmem, dah, dwl, idesc, 1u);
+                            um_mma(d_tmem, dah, dwh, idesc, 1u);
+                            first = 1u;
+                            dwh += (uint64_t)(N * 4);
+                            if (SPT == 1 || ++gq == SPT) { gq = 0; tap_off16 += step_tap16; }
+                        }
+                        um_commit(&w_empty[slot]);
+                        if (s1 == jb.steps) um_commit(&d_ready[c]);
+                    }
+                    // the other lanes advance the same counters
+                    const uint32_t adv = (uint32_t)(s1 - s0);
+                    {
+                        uint32_t t_adv = (gq + adv) / SPT;   // only the elected lane modified gq / tap_off16 above: recompute for all
+                        (void)t_adv;
+                    }
+                    __syncwarp();
+                    // broadcast the elected lane's running state (it is the only one that advanced it)
+                    {
+                        const uint32_t steps_done = (uint32_t)s1;
+                        gq = steps_done % SPT;
+                        tap_off16 = (steps_done / SPT) * step_tap16;
+                        first = 1u;
+                    }
+                }
+                if (lane == 0) UM_TRACE(ji * 4 + 1);
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================== epilogue (thread = time row x 8-channel group) ===========================
+        // G groups of 4 warps; group g owns channels 8g .. 8g+7 of all 128 rows (a warp may only touch the TMEM lane
+        // quadrant warp % 4, so each group is one full set of quadrants)
+        constexpr int NE = 128 * G;
+        const int et = tid - 128, g = (warp - 4) >> 2, quad = warp & 3, p = quad * 32 + lane;   // p: tile row = TMEM lane
+        const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+        uint32_t* xh = reinterpret_cast<uint32_t*>(sm + L::xin);
+        uint32_t* xl = xh + (NJ + 16) * PWI;
+        float* x0 = reinterpret_cast<float*>(sm + L::x0);
+        const size_t boff = (size_t)b * a.in_bstride;
+        float* dst = a.out + (size_t)b * a.n_out * C;
+        uint32_t d_seen[3] = {0, 0, 0};
+        auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(NE) : "memory"); };
+
+        // writes this thread's 8 channels of its row (already activated) into operand buffer `buf` (rows R, tile starts
+        // at row `lead`), and the tail rows additionally into the saved context `ctx` (ctx_rows rows)
+        auto write_rows = [&](int buf_off, int R, int lead, const float* y, int ctx_off, int ctx_rows) {
+            um_store8(sm + buf_off, G * R * 16, g * R + lead + p, y);
+            const int cr = p - (UM_TT - ctx_rows);
+            if (cr >= 0) um_store8(sm + ctx_off, G * ctx_rows * 16, g * ctx_rows + cr, y);
+        };
+        // copies the saved context (ctx_rows rows) in front of the tile rows of an operand buffer
+        auto restore = [&](int buf_off, int R, int lead, int ctx_off, int ctx_rows) {
+            if (p < ctx_rows) {
+#pragma unroll
+                for (int part = 0; part < 2; ++part)
+                    *reinterpret_cast<uint4*>(sm + buf_off + part * G * R * 16 + (g * R + lead - ctx_rows + p) * 16) =
+                        *reinterpret_cast<const uint4*>(sm + ctx_off + part * G * ctx_rows * 16 + (g * ctx_rows + p) * 16);
+            }
+        };
+        auto publish = [&](int c) {   // operand buffer of chain c is complete: hand it to the MMA warp
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) um_arrive(&a_ready[c]);
+        };
+        auto load8 = [&](const float* ptr, float* o) {
+            const float4 u0 = __ldg(reinterpret_cast<const float4*>(ptr + 8 * g)), u1 = __ldg(reinterpret_cast<const float4*>(ptr + 8 * g) + 1);
+            o[0] = u0.x; o[1] = u0.y; o[2] = u0.z; o[3] = u0.w; o[4] = u1.x; o[5] = u1.y; o[6] = u1.z; o[7] = u1.w;
+        };
+        auto a1_off = [&](int c) { return c == 0 ? L::a1(0) : c == 1 ? L::a1(1) : L::a1(2); };
+        auto a2_off = [&](int c) { return c == 0 ? L::a2(0) : c == 1 ? L::a2(1) : L::a2(2); };
+        // context of the dilated conv of layer l: rows (K-1) d_l, stored after those of the earlier layers
+        auto c1_off = [&](int c, int l) {
+            const int K = um_K(c), rows_before = (K - 1) * (l == 0 ? 0 : l == 1 ? 1 : 4);
+            return (c == 0 ? L::c1(0) : c == 1 ? L::c1(1) : L::c1(2)) + 2 * G * rows_before * 16;
+        };
+        auto c2_off = [&](int c, int l) {
+            const int K = um_K(c);
+            return (c == 0 ? L::c2(0) : c == 1 ? L::c2(1) : L::c2(2)) + 2 * G * (K - 1) * l * 16;
+        };
+
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            const int t0 = t_first + tile * UM_TT;
+            if (et == 0) UM_TRACE(72);
+            // ---- stage input rows j0-1 .. j0+TT/U-1: mean of the producer's partials, split to bf16 hi/lo ----
+            {
+                const int j_base = t0 / U - 1;
+                constexpr int V = CIN / 4;
+                for (int i = et; i < NJ * V; i += NE) {
+                    const int jj = i / V, c4 = i - jj * V;
+                    const int j = j_base + jj;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j >= 0 && j < a.n_in) {
+                        const size_t o = boff + (size_t)j * CIN + c4 * 4;
+                        v = __ldg(reinterpret_cast<const float4*>(a.in_p[0] + o));
+                        if (a.n_parts == 3) {
+                            const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.in_p[1] + o));
+                            const float4 v2 = __ldg(reinterpret_cast<const float4*>(a.in_p[2] + o));
+                            v.x = ((v.x + v1.x) + v2.x) / 3.0f; v.y = ((v.y + v1.y) + v2.y) / 3.0f;
+                            v.z = ((v.z + v1.z) + v2.z) / 3.0f; v.w = ((v.w + v1.w) + v2.w) / 3.0f;
+                        }
+                    }
+                    uint32_t h0, l0, h1, l1;
+                    split_pair(v.x, v.y, h0, l0);
+                    split_pair(v.z, v.w, h1, l1);
+                    *reinterpret_cast<uint2*>(xh + jj * PWI + c4 * 2) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(xl + jj * PWI + c4 * 2) = make_uint2(l0, l1);
+                }
+            }
+            epi_bar();
+            // ---- ConvTranspose1d as U phase convolutions (mma.sync, all epilogue warps) -> x0[128][C] ----
+            {
+                constexpr int KC_UP = (2 * CIN) / 16, NT = C / 8;
+                const int rows = UM_TT / U, tiles = (rows + 15) / 16;
+                float2 bup[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) bup[nt] = __ldg(reinterpret_cast<const float2*>(a.b_up + nt * 8 + 2 * (tid & 3)));
+                const uint32_t xh_a = um_smem_u32(xh), xl_a = um_smem_u32(xl);
+                for (int item = warp - 4; item < U * tiles; item += 4 * G) {
+                    const int r = item / tiles, tl = item - r * tiles;
+                    const uint2* wh = a.upf_h + (size_t)r * KC_UP * NT * 32;
+                    const uint2* wl = a.upf_l + (size_t)r * KC_UP * NT * 32;
+                    mma_rows<CIN, C, 2, 1>(xh_a, xl_a, 1, wh, wl, 1, tl * 16, [&](int row, int nt, int co, float v0, float v1) {
+                        if (row < rows) *reinterpret_cast<float2*>(x0 + (U * row + r) * PX + co) = make_float2(v0 + bup[nt].x, v1 + bup[nt].y);
+                    });
+                }
+            }
+            // contexts of the first dilated convs (layer 0) in front of the tiles
+#pragma unroll
+            for (int c = 0; c < 3; ++c) restore(a1_off(c), um_R1(c), (um_K(c) - 1) * 5, c1_off(c, 0), (um_K(c) - 1) * 1);
+            epi_bar();
+            // ---- x of the three resblocks = x0 (TMEM) and their first conv inputs ----
+            float xr[8];
+            {
+                const float4 u0 = *reinterpret_cast<const float4*>(x0 + p * PX + 8 * g), u1 = *reinterpret_cast<const float4*>(x0 + p * PX + 8 * g + 4);
+                xr[0] = u0.x; xr[1] = u0.y; xr[2] = u0.z; xr[3] = u0.w; xr[4] = u1.x; xr[5] = u1.y; xr[6] = u1.z; xr[7] = u1.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                um_st8(t_lane + c * 2 * N + 8 * g, xr);
+                float ea[8], ieb[8], y[8];
+                load8(a.ea[c][0], ea);
+                load8(a.ieb[c][0], ieb);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = snake_fast(xr[i], ea[i], ieb[i]);
+                write_rows(a1_off(c), um_R1(c), (um_K(c) - 1) * 5, y, c1_off(c, 0), (um_K(c) - 1) * 1);
+                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                publish(c);
+            }
+
+            if (et == 0) UM_TRACE(73);
+            float osum[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) osum[i] = 0.f;
+#pragma unroll 1
+            for (int ji = 0; ji < 18; ++ji) {
+                const UmmaJob jb = a.w.jobs[ji];
+                const int c = jb.chain, l = jb.layer, K = jb.K;
+                float v[8], pa[8], ea[8], ieb[8];
+                // per-channel constants of this job are fetched while the MMAs are still running
+                if (!jb.conv2) {
+                    load8(a.w.b1[c][l], pa); load8(a.ea[c][2 * l + 1], ea); load8(a.ieb[c][2 * l + 1], ieb);
+                } else {
+                    load8(a.w.bsum[c][l], pa);
+                    if (l < 2) { load8(a.ea[c][2 * (l + 1)], ea); load8(a.ieb[c][2 * (l + 1)], ieb); }
+                }
+                um_wait(&d_ready[c], d_seen[c] & 1);
+                ++d_seen[c];
+                if (et == 0) UM_TRACE(ji * 4 + 2);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                if (!jb.conv2) {
+                    // dilated conv done: + bias -> SnakeBeta -> input of the second conv
+                    restore(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, c2_off(c, l), K - 1);
+                    um_ld8(t_lane + c * 2 * N + N + 8 * g, v);
+                    epi_bar();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
+                    write_rows(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, v, c2_off(c, l), K - 1);
+                    publish(c);
+                } else {
+                    // residual stream updated in TMEM: x_true = x + (sum of the second convs' biases so far)
+                    const int ctx = (K - 1) * (l == 0 ? 3 : 5);
+                    if (l < 2) restore(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, c1_off(c, l + 1), ctx);
+                    um_ld8(t_lane + c * 2 * N + 8 * g, v);
+                    epi_bar();
+                    if (l < 2) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
+                        write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, v, c1_off(c, l + 1), ctx);
+                        publish(c);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) osum[i] += v[i] + pa[i];
+                        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                    }
+                }
+                if (et == 0) UM_TRACE(ji * 4 + 3);
+            }
+            // ---- mean of the three resblocks, channel-last (warm-up tiles are not written) ----
+            const int tg = t0 + p;
+            if (t0 >= t_begin && tg < t_end) {
+                float4* o = reinterpret_cast<float4*>(dst + (size_t)tg * C + 8 * g);
+                o[0] = make_float4(osum[0] / 3.0f, osum[1] / 3.0f, osum[2] / 3.0f, osum[3] / 3.0f);
+                o[1] = make_float4(osum[4] / 3.0f, osum[5] / 3.0f, osum[6] / 3.0f, osum[7] / 3.0f);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((uint32_t)L::tmem_cols));
+    }
+}
+
+template <int C, int U>
+int launch_stage_umma(const UmmaStageArgs& a, int B, cudaStream_t stream) {
+    using L = UmLayout<C, U>;
+    static int sms = 0;
+    if (!sms) {
+        BVC_CUDA(cudaFuncSetAttribute(stage_umma_kernel<C, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
+        int dev = 0;
+        BVC_CUDA(cudaGetDevice(&dev));
+        BVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // time ranges per utterance: ~4 waves of CTAs, but ranges long enough that their warm-up (120 samples) stays small
+    const int tiles_total = (a.n_out + UM_TT - 1) / UM_TT;
+    const int want = (4 * sms + B - 1) / B;
+    const int max_ranges = tiles_total / 4 > 0 ? tiles_total / 4 : 1;
+    int ranges = want < max_ranges ? want : max_ranges;
+    if (ranges < 1) ranges = 1;
+    const int tiles_per = (tiles_total + ranges - 1) / ranges;
+    ranges = (tiles_total + tiles_per - 1) / tiles_per;
+    stage_umma_kernel<C, U><<<dim3(ranges, B), 128 + 128 * L::G, L::total, stream>>>(a);
+    BVC_CHECK_LAUNCH();
+    return BVC_OK;
+}
+
 struct PostArgs {
+    int n_parts;            // 3: mean of three partial tensors, 1: a single tensor
     const float* in_p[3];   // [B, n, C] channel-last
     int n;
     int n_out;              // min(length, n)
@@ -573,7 +1087,8 @@ __global__ void __launch_bounds__(kThreads) post_kernel(PostArgs a) {
         float v = 0.f;
         if (tg >= 0 && tg < a.n) {
             const size_t o = boff + (size_t)tg * C + c;
-            const float x = ((__ldg(a.in_p[0] + o) + __ldg(a.in_p[1] + o)) + __ldg(a.in_p[2] + o)) / 3.0f;
+            const float x = a.n_parts == 1 ? __ldg(a.in_p[0] + o)
+                                           : ((__ldg(a.in_p[0] + o) + __ldg(a.in_p[1] + o)) + __ldg(a.in_p[2] + o)) / 3.0f;
             v = snake(x, __ldg(a.ea + c), __ldg(a.ieb + c));
         }
         s[c][p] = v;
@@ -700,7 +1215,59 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
     }
 
     static const int kTT[4] = {128, 256, 256, 512};
+    // Stages that run on the tcgen05 kernel (bit i = stage i).  Its MMAs fetch the 128 x 16 activation operand from
+    // shared memory for every instruction (~64 clk measured), so with N = C_out it sustains ~40 C_out MAC/clk: twice the
+    // mma.sync kernel at C = 32, on par at 16, behind at 8 where the per-job epilogue latency dominates.  Default: stage 1.
+    static const int umma_mask = getenv("BVC_VOC_UMMA") ? atoi(getenv("BVC_VOC_UMMA")) : 0x2;
+    bool single[4] = {false, false, false, false};     // stage i wrote one tensor (the mean) instead of three partials
     for (int i = 0; i < 4; ++i) {
+        if (precision >= 1 && ((umma_mask >> i) & 1) && i >= 1 && w.umma[i].ready) {
+            // all three resblocks of the stage in one tcgen05 kernel; the output is their mean
+            UmmaStageArgs ua;
+            ua.n_parts = single[i - 1] ? 1 : 3;
+            for (int q = 0; q < 3; ++q) ua.in_p[q] = vb.part[i - 1][single[i - 1] ? 0 : q];
+            ua.in_bstride = (long long)vb.n[i] * vb.C[i];
+            ua.n_in = (int)vb.n[i];
+            ua.n_out = (int)vb.n[i + 1];
+            ua.b_up = w.b_up[i];
+            ua.upf_h = w.upf_h[i];
+            ua.upf_l = w.upf_l[i];
+            for (int cc = 0; cc < 3; ++cc) {
+                const AmpBlockWeights& bw = w.blocks[i * 3 + (2 - cc)];
+                for (int q = 0; q < 6; ++q) { ua.ea[cc][q] = bw.act[q].ea; ua.ieb[cc][q] = bw.act[q].inv_eb; }
+            }
+            ua.out = vb.part[i][0];
+            ua.w = w.umma[i];
+            ua.trace = nullptr;
+            static unsigned long long* trace_dev = nullptr;
+            const bool tracing = getenv("BVC_VOC_TRACE") && atoi(getenv("BVC_VOC_TRACE")) == i;
+            if (tracing) {
+                if (!trace_dev) BVC_CUDA(cudaMalloc(&trace_dev, 80 * sizeof(unsigned long long)));
+                BVC_CUDA(cudaMemsetAsync(trace_dev, 0, 80 * sizeof(unsigned long long), stream));
+                ua.trace = trace_dev;
+            }
+            int rc;
+            switch (vb.C[i + 1]) {
+                case 32: rc = launch_stage_umma<32, 8>(ua, B, stream); break;
+                case 16: rc = launch_stage_umma<16, 2>(ua, B, stream); break;
+                default: rc = launch_stage_umma<8, 2>(ua, B, stream); break;
+            }
+            if (rc != BVC_OK) return rc;
+            if (tracing) {   // per job: MMA warp got the operand / issued all MMAs, epilogue saw the result / finished
+                unsigned long long hbuf[80];
+                BVC_CUDA(cudaStreamSynchronize(stream));
+                BVC_CUDA(cudaMemcpy(hbuf, trace_dev, sizeof(hbuf), cudaMemcpyDeviceToHost));
+                const unsigned long long z = hbuf[72];
+                fprintf(stderr, "stage %d tile trace (us): prologue %.2f\n", i, (hbuf[73] - z) / 1e3);
+                for (int ji = 0; ji < 18; ++ji)
+                    fprintf(stderr, "  job %2d chain %d layer %d conv%d steps %2d: mma_start %6.2f mma_issued %6.2f epi_start %6.2f epi_done %6.2f\n", ji,
+                            ua.w.jobs[ji].chain, ua.w.jobs[ji].layer, ua.w.jobs[ji].conv2 + 1, ua.w.jobs[ji].steps, (hbuf[ji * 4] - z) / 1e3,
+                            (hbuf[ji * 4 + 1] - z) / 1e3, (hbuf[ji * 4 + 2] - z) / 1e3, (hbuf[ji * 4 + 3] - z) / 1e3);
+            }
+            vb.part[i][1] = vb.part[i][2] = vb.part[i][0];   // parity taps read "three partials": all the same mean
+            single[i] = true;
+            continue;
+        }
         for (int jj = 0; jj < 3; ++jj) {
             const int j = 2 - jj;   // largest kernel first
             const AmpBlockWeights& bw = w.blocks[i * 3 + j];
@@ -710,8 +1277,8 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
                 a.in_p[0] = a.in_p[1] = a.in_p[2] = vb.pre;
                 a.in_bstride = (long long)(T + 6) * w.c0;
             } else {
-                a.n_parts = 3;
-                for (int q = 0; q < 3; ++q) a.in_p[q] = vb.part[i - 1][q];
+                a.n_parts = single[i - 1] ? 1 : 3;
+                for (int q = 0; q < 3; ++q) a.in_p[q] = vb.part[i - 1][single[i - 1] ? 0 : q];
                 a.in_bstride = (long long)vb.n[i] * vb.C[i];
             }
             a.n_in = (int)vb.n[i];
@@ -742,6 +1309,7 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
     }
     {
         PostArgs p;
+        p.n_parts = single[3] ? 1 : 3;
         for (int q = 0; q < 3; ++q) p.in_p[q] = vb.part[3][q];
         p.n = (int)vb.n[4];
         p.n_out = length < p.n ? length : p.n;
