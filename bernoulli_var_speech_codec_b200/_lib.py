@@ -42,6 +42,7 @@ SYMBOLS = {
     "bvc_set_frontend": (C.c_int, [_P, _P, _P]),
     "bvc_logmel": (C.c_int, [_P, _P, _I, _I, _F, _P, _P]),
     "bvc_encode": (C.c_int, [_P, _P, _P, _F, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "bvc_unpack_codes": (C.c_int, [_P, _P, _P, _F, _I, _I, _P, _P]),
     "bvc_decode_mel": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "bvc_vocode": (C.c_int, [_P, _P, _I, _I, _I, _F, _P, _P]),
     "bvc_vocoder_out_len": (C.c_int64, [_P, _I]),
@@ -52,6 +53,7 @@ SYMBOLS = {
     "bvc_workspace_bytes": (C.c_size_t, [_P]),
     "bvc_kernel_launches": (C.c_int64, [_P]),
     "bvc_set_precision": (C.c_int, [_P, _I]),
+    "bvc_last_recurrent_ms": (C.c_float, [_P]),
     "bvc_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
 }
 

@@ -208,6 +208,15 @@ class _Engine:
                                            _stream(dev)), "BVRNN.encode")
         return codes, all_h, h_fin, logits, packed
 
+    def unpack_codes(self, packed, bits, bits_scalar):
+        """packed int64 [B, T] (bit i = code i) -> float codes [B, T, Z] with 0.5 for masked bits."""
+        B, T = packed.shape
+        packed = packed.contiguous()
+        codes = torch.empty(B, T, self.Z, device=packed.device, dtype=torch.float32)
+        _lib.check(self.lib.bvc_unpack_codes(self.handle, _ptr(packed), _ptr(bits), float(bits_scalar), B, T, _ptr(codes),
+                                             _stream(self.device)), "unpack_codes")
+        return codes
+
     def decode_mel(self, codes, h0):
         codes = self._dev(codes, "z")
         B, T, _ = codes.shape
@@ -254,6 +263,10 @@ class _Engine:
 
     def kernel_launches(self):
         return int(self.lib.bvc_kernel_launches(self.handle))
+
+    def last_recurrent_ms(self):
+        """Device time of the persistent recurrent kernel of the last encode / decode_mel call (CUDA events)."""
+        return float(self.lib.bvc_last_recurrent_ms(self.handle))
 
     def set_precision(self, mode):
         _lib.check(self.lib.bvc_set_precision(self.handle, int(mode)), "set_precision")
@@ -354,6 +367,23 @@ class BVRNNCodecModel(nn.Module):
     def forward(self, x, bitrate):
         length = x.shape[1]
         codes = self.encode(x, bitrate)
+        return self.decode(codes, length)
+
+    # ---- packed wire format (not in the reference, which moves 256 B of floats per 35-bit frame) ----
+    def encode_packed(self, x, bitrate):
+        """x (B, L) CUDA tensor -> (packed int64 (B, L // hop), bits per frame); bit i of a word is code i."""
+        bits = self.bits_per_frame(bitrate)
+        mel = self._engine.logmel(x.to(self.device), SCALING)
+        _, _, _, _, packed = self._engine.encode(mel, None, bits, None, want_all_h=False, want_packed=True)
+        return packed, bits
+
+    def decode_packed(self, packed, bits, length):
+        """Inverse of encode_packed: packed int64 (B, T), bits per frame (number or (B, T) tensor) -> waveform (B, length)."""
+        packed = packed.to(self.device)
+        if torch.is_tensor(bits):
+            codes = self._engine.unpack_codes(packed, bits.to(self.device, torch.float32).contiguous(), 0.0)
+        else:
+            codes = self._engine.unpack_codes(packed, None, float(bits))
         return self.decode(codes, length)
 
     # ---- taps used by the parity tests (not part of the reference API) ----

@@ -789,6 +789,16 @@ int bvc_encode(bvc_handle* h, const float* mel_dev, const float* bits_dev, float
     return ws_release(h, (cudaStream_t)stream);
 }
 
+int bvc_unpack_codes(bvc_handle* h, const uint64_t* packed_dev, const float* bits_dev, float bits_scalar, int32_t B,
+                     int32_t T, float* codes_dev, void* stream) {
+    REQUIRE(h && packed_dev && codes_dev, BVC_ERR_INVALID, "bvc_unpack_codes: null argument");
+    REQUIRE(B > 0 && T >= 0, BVC_ERR_INVALID, "bvc_unpack_codes: bad B/T");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    return unpack_codes((const unsigned long long*)packed_dev, bits_dev, bits_scalar, h->cfg.var_bit, (size_t)B * T,
+                        h->cfg.z_dim, codes_dev, (cudaStream_t)stream);
+}
+
 int bvc_decode_mel(bvc_handle* h, const float* codes_dev, const float* h0_dev, int32_t B, int32_t T, float* mel_dev,
                    float* h_final_dev, void* stream) {
     REQUIRE(h && codes_dev && mel_dev, BVC_ERR_INVALID, "bvc_decode_mel: null argument");
@@ -889,6 +899,8 @@ int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T
     BVC_CUDA(cudaStreamSynchronize(s));
     return BVC_OK;
 }
+
+float bvc_last_recurrent_ms(const bvc_handle* h) { return h ? h->bw.rw.last_kernel_ms : 0.f; }
 
 int bvc_host_alloc(void** out, size_t bytes) {
     REQUIRE(out && bytes > 0, BVC_ERR_INVALID, "bvc_host_alloc: bad argument");

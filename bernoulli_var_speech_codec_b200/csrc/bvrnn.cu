@@ -80,6 +80,19 @@ __global__ void normalize_kernel(const float* __restrict__ y, const float* __res
     out[idx] = (y[idx] - mean[c]) / std[c];
 }
 
+// packed word -> the reference's float code vector: bit i < budget -> {0, 1}, masked bits -> 0.5 (bvrnn.py:191-196)
+__global__ void __launch_bounds__(256)
+unpack_codes_kernel(const unsigned long long* __restrict__ packed, const float* __restrict__ bits, float bits_scalar,
+                    int var_bit, size_t n_frames, int Z, float* __restrict__ codes) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_frames * (size_t)Z) return;
+    const size_t f = idx / Z;
+    const int i = (int)(idx - f * Z);
+    const float budget = bits ? bits[f] : bits_scalar;
+    const bool active = !var_bit || (budget > (float)i);
+    codes[idx] = active ? (float)((packed[f] >> i) & 1ull) : 0.5f;
+}
+
 struct Lin {
     const LinearWeights* w;
     const float* bias;
@@ -105,6 +118,16 @@ int run_linear(const float* A, int lda, int M, const LinearWeights& w, const flo
     } while (0)
 
 }  // namespace
+
+int unpack_codes(const unsigned long long* packed, const float* bits, float bits_scalar, int var_bit, size_t n_frames,
+                 int Z, float* codes, cudaStream_t s) {
+    if (Z > 64) { set_error("unpack_codes: z_dim > 64 does not fit a 64-bit word"); return BVC_ERR_INVALID; }
+    const size_t n = n_frames * (size_t)Z;
+    if (n == 0) return BVC_OK;
+    unpack_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(packed, bits, bits_scalar, var_bit, n_frames, Z, codes);
+    BVC_CHECK_LAUNCH();
+    return BVC_OK;
+}
 
 size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T) {
     const size_t BT = (size_t)B * T, H = w.H;
@@ -368,10 +391,17 @@ int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
         pb.p->trace_frames = trace_frames;
     }
     BVC_CUDA(cudaMemcpyAsync(w.rw.prog_dev, w.rw.prog_host, sizeof(rec::Program), cudaMemcpyHostToDevice, s));
+    if (!w.rw.ev_begin) {
+        BVC_CUDA(cudaEventCreate(&w.rw.ev_begin));
+        BVC_CUDA(cudaEventCreate(&w.rw.ev_end));
+    }
+    BVC_CUDA(cudaEventRecord(w.rw.ev_begin, s));
     int rc = rec::launch(w.rw.prog_dev, pb.n_clusters, w.rw.sync_words, s);
     if (rc) return rc;
+    BVC_CUDA(cudaEventRecord(w.rw.ev_end, s));
     // prog_host is overwritten by the next call, and a failed kernel must be reported by this one
     BVC_CUDA(cudaStreamSynchronize(s));
+    BVC_CUDA(cudaEventElapsedTime(&w.rw.last_kernel_ms, w.rw.ev_begin, w.rw.ev_end));
     if (trace_dev) {
         std::vector<unsigned long long> hbuf(trace_n);
         BVC_CUDA(cudaMemcpy(hbuf.data(), trace_dev, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));

@@ -114,6 +114,9 @@ struct RecurrentWeights {
     // W_ih_z phi_z + b [B,3H] of the LAST frame, the latter two with gate-interleaved columns
     const float *tap_dh = nullptr, *tap_gh = nullptr, *tap_giz = nullptr;
     int tap_B = 0;
+    // device time of the last persistent-kernel launch (CUDA events on the launching stream): bench.py's roofline
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    float last_kernel_ms = 0.f;
 };
 
 struct BvrnnWeights {
@@ -145,6 +148,8 @@ struct Workspace {
 };
 
 size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T);
+int unpack_codes(const unsigned long long* packed, const float* bits, float bits_scalar, int var_bit, size_t n_frames,
+                 int Z, float* codes, cudaStream_t s);
 int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
                  float* all_h, float* h_final, int precision, cudaStream_t stream);

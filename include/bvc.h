@@ -117,6 +117,12 @@ int bvc_encode(bvc_handle* h, const float* mel_dev, const float* bits_dev, float
                float* codes_dev, uint64_t* packed_dev, float* logits_dev,
                float* all_h_dev, float* h_final_dev, void* stream);
 
+/* Wire format (new; the reference only has the float layout): one uint64 per frame, bit i = code i, masked bits 0.
+ * bvc_encode fills packed_dev; this expands it back to the reference's float codes ({0,1}, 0.5 for bits >= budget,
+ * bvrnn.py:191-196) so that bvc_decode_mel can consume it.  bits_dev [B,T] or NULL -> bits_scalar. */
+int bvc_unpack_codes(bvc_handle* h, const uint64_t* packed_dev, const float* bits_dev, float bits_scalar,
+                     int32_t B, int32_t T, float* codes_dev, void* stream);
+
 /* bvrnn.py:211-229 (BVRNN.decode).  codes_dev [B,T,z_dim] arbitrary floats. */
 int bvc_decode_mel(bvc_handle* h, const float* codes_dev, const float* h0_dev,
                    int32_t B, int32_t T, float* mel_dev, float* h_final_dev, void* stream);
@@ -148,6 +154,9 @@ int bvc_host_free(void* p);
 size_t bvc_workspace_bytes(const bvc_handle* h);
 /* Kernels launched by this library since the handle was created (bench evidence). */
 int64_t bvc_kernel_launches(const bvc_handle* h);
+/* Device time in ms (CUDA events on the launching stream) of the persistent recurrent kernel launched by the last
+ * bvc_encode / bvc_decode_mel (or their _host variants): the dominant kernel of the path, used for bench.py's roofline. */
+float bvc_last_recurrent_ms(const bvc_handle* h);
 /* Arithmetic mode of the GEMM/conv inner products: 1 = split-bf16 tensor core (default; the benchmarked path),
  * 0 = fp32 FFMA kernels (slow cross-check path with reference-grade rounding). */
 int bvc_set_precision(bvc_handle* h, int32_t mode);

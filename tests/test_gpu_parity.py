@@ -193,3 +193,31 @@ def test_larger_batch_properties(model_var, oracle_var):
     perm = torch.randperm(B)
     assert torch.equal(model_var.encode(xd[perm].contiguous(), 3000), codes[perm])
     _check_case(model_var, oracle_var, x[:2], 3000)
+
+
+def test_packed_wire_format_round_trip(model_var, model_fix, oracle_var):
+    """encode_packed / decode_packed (uint64 per frame) reproduce the float-code path bit for bit, for every budget edge."""
+    x = _noise(3, 9000, 77).to(model_var.device)
+    for bitrate in (0, 86.2, 3000, 5512.5, 9000):          # 0, 1, 35, 64, >64 bits per frame
+        codes = model_var.encode(x, bitrate)
+        packed, bits = model_var.encode_packed(x, bitrate)
+        assert packed.dtype == torch.int64 and packed.shape == codes.shape[:2]
+        assert torch.equal(model_var._engine.unpack_codes(packed, None, bits), codes)
+        nb = int(min(max(bits, 0), 64))
+        if nb < 64:
+            assert (packed >> nb == 0).all()                  # masked bits are never set in the word
+        assert torch.equal(model_var.decode_packed(packed, bits, x.shape[1]), model_var.decode(codes, x.shape[1]))
+    # per-frame budgets through the packed path (reference bvrnn.py:180-182 takes varBitrate[B, T])
+    T = x.shape[1] // 256
+    vb = torch.randint(0, 65, (3, T), generator=torch.Generator().manual_seed(5)).float().to(model_var.device)
+    mel = model_var._engine.logmel(x, 10 ** (-10 / 20))
+    codes, _, _, _, packed = model_var._engine.encode(mel, vb, 0.0, None, want_all_h=False, want_packed=True)
+    assert torch.equal(model_var._engine.unpack_codes(packed, vb, 0.0), codes)
+    from oracle.codec_oracle import bvrnn_encode as oracle_bvrnn_encode
+    with torch.no_grad():
+        o_codes = oracle_bvrnn_encode(oracle_var.sd, mel.cpu(), vb.cpu(), torch.zeros(3, 1024), True)[0]
+    assert ((codes.cpu() == 0.5) == (o_codes == 0.5)).all()             # masks follow the per-frame budgets exactly
+    assert (codes.cpu() == o_codes).float().mean() > 0.999              # bits: up to threshold-band flips (and their wake)
+    # fixed-rate model: every bit is active whatever the budget says
+    pk, bits = model_fix.encode_packed(x, 3000)
+    assert torch.equal(model_fix._engine.unpack_codes(pk, None, bits), model_fix.encode(x, 3000))
