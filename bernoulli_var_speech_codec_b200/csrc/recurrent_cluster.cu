@@ -468,6 +468,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     unsigned* counter = sync_words + 32 * (1 + m_tile);
     unsigned long long* trace = prog->trace;
     const int trace_frames = prog->trace_frames;
+    const int dbg_flags = prog->debug_flags;
 
     if (tid == 0) {
         for (int i = 0; i < A_SLOTS; ++i) mbar_init(&bars.fullA[i], 1);
@@ -709,7 +710,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                 }
                 // ---- end of phase: publish this CTA's outputs to the m-tile's barrier domain ----
                 if (tid == 128) BVC_TRACE(12);
-                fence_proxy_async_all();                                  // they are read by other CTAs' bulk copies
+                // The outputs are read by other CTAs' bulk copies (async proxy).  The release below is cumulative over the
+                // barrier (the CUTLASS semaphore pattern), and the consumer's copy thread issues fence.proxy.async after its
+                // acquire, before the bulk copies.  A writer-side fence.proxy.async here would be a MEMBAR.ALL.GPU in each of
+                // the 128 epilogue threads on the critical path of every phase.
+                if (dbg_flags & 32) fence_proxy_async_all();
                 {   // barrier over the 4 epilogue warps; a failed wait anywhere retires all of them together
                     uint32_t any;
                     asm volatile(
@@ -722,7 +727,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         : "memory");
                     dead = any != 0;
                 }
-                if (tid == 128 && !(prog->debug_flags & 8)) {
+                if (tid == 128) {
                     // The counter is monotonic over all phases, so nobody may arrive for phase p before every CTA
                     // of the domain has arrived for phase p - 1.  A CTA with work in phase p got that from its
                     // copy thread (which waited for it before loading activations); an idle CTA waits here.
