@@ -406,7 +406,9 @@ int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
         std::vector<unsigned long long> hbuf(trace_n);
         BVC_CUDA(cudaMemcpy(hbuf.data(), trace_dev, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         cudaFree(trace_dev);
-        if (FILE* f = fopen(trace_path, "wb")) {
+        static int trace_no = 0;     // one file per launch: <path>.0 (first encode), <path>.1 (first decode), ...
+        const std::string path = std::string(trace_path) + "." + std::to_string(trace_no++);
+        if (FILE* f = fopen(path.c_str(), "wb")) {
             const int hdr[4] = {n_ctas, trace_frames, rec::MAX_PHASES, rec::TRACE_EVENTS};
             fwrite(hdr, sizeof(int), 4, f);
             fwrite(hbuf.data(), sizeof(unsigned long long), trace_n, f);
