@@ -567,7 +567,9 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     if (lane == 0) BVC_TRACE(2);
                     if (!dead) {
                         if (elect_one()) {
-                            fence_proxy_async_all();   // the producers' generic-proxy stores -> this thread's async-proxy reads
+                            // the producers' generic-proxy stores (acquired above) -> this thread's async-proxy reads of global
+                            // memory; the .global form is a bare FENCE.VIEW.ASYNC.G, the unqualified one adds a MEMBAR.ALL.GPU
+                            asm volatile("fence.proxy.async.global;\n" ::: "memory");
                             for (int c = 0; c < nck; ++c) {
                                 mbar_expect_tx(&bars.fullA[c], ACT_CHUNK_BYTES);
                                 bulk_g2s(smem_base + SMEM_A + c * ACT_CHUNK_BYTES, src + (size_t)c * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES,
