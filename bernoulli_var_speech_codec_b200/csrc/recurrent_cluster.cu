@@ -37,7 +37,7 @@ namespace rec {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;                                // MMA warp, copy warp, 2 spare, 8 epilogue warps
 constexpr int A_SLOTS = 4;                                   // chunks of the resident activation quarter
 constexpr int W_SLOTS = 4;
 constexpr int W_SLOT_BYTES = 2 * 64 * 128;                   // bn <= 64
@@ -57,7 +57,7 @@ struct Bars {
     uint64_t fullW[W_SLOTS];       // weight chunk landed (expect_tx)
     uint64_t emptyW[W_SLOTS];      // weight chunk consumed (tcgen05.commit)
     uint64_t accFull[ACC_SLOTS];   // accumulator complete (tcgen05.commit)
-    uint64_t accEmpty[ACC_SLOTS];  // accumulator drained (4 epilogue warps)
+    uint64_t accEmpty[ACC_SLOTS];  // accumulator drained (8 epilogue warps)
     uint64_t aFree;                // all MMAs of the job retired: activation buffer reusable
     uint64_t stgFull;              // the 3 peers' partials have landed in my staging buffer (expect_tx / st.async complete_tx)
     uint64_t stgEmpty;             // the 3 peers finished reading their staging buffer
@@ -424,6 +424,129 @@ __device__ __forceinline__ void reduce_parts(const float* own, int rank, int row
     }
 }
 
+// ---- 8-column variants: a 64-wide tile is finished by TWO threads per row (column halves hf = 0 / 1 of every quarter) ----
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void load8_cg(const float* p, float* v) {
+    const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+// 8 consecutive values of activation row `row` (columns col0 .. col0+7, col0 % 8 == 0) -> one 16-byte piece of hi and of lo
+__device__ __forceinline__ void store_img8(unsigned char* img, int m_tile, int kchunks, int row, int col0, const float* v, bool zero_lo) {
+    unsigned char* base = img + ((size_t)m_tile * kchunks + (col0 >> 6)) * ACT_CHUNK_BYTES + row * 128 +
+                          ((((col0 & 63) >> 3) ^ (row & 7)) << 4);
+    uint4 h, l;
+    split_pair(v[0], v[1], h.x, l.x); split_pair(v[2], v[3], h.y, l.y);
+    split_pair(v[4], v[5], h.z, l.z); split_pair(v[6], v[7], h.w, l.w);
+    if (zero_lo) l = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(base) = h;
+    *reinterpret_cast<uint4*>(base + ACT_PART_BYTES) = l;
+}
+struct Prefetch8 {
+    float a[8];      // bias + addend
+    float budget;    // BOTTLENECK: bit budget of (m, t)
+};
+__device__ __forceinline__ void prefetch8(const Op& op, const Frame& fr, int t, int m, int col0, Prefetch8& pf) {
+    if (m >= fr.M) return;
+    if (op.bias) load8_cg(op.bias + col0, pf.a);
+    else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pf.a[i] = 0.f;
+    }
+    if (op.addend) {
+        float tmp[8];
+        load8_cg(op.addend + (size_t)t * op.add_tstride + (size_t)m * op.ldadd + col0, tmp);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pf.a[i] += tmp[i];
+    }
+    if (op.kind == KIND_BOTTLENECK) pf.budget = fr.bits ? __ldg(fr.bits + (size_t)m * fr.T + t) : fr.bits_scalar;
+}
+// Epilogue of 8 output columns (col0 .. col0+7) of row m.  v = A.W^T summed over the whole K.
+__device__ __forceinline__ void finalize8(const Op& op, const Frame& fr, int t, int m, int row, int m_tile, int col0, float* v,
+                                          const Prefetch8& pf) {
+    if (m >= fr.M) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += pf.a[i];
+    if (op.kind == KIND_BOTTLENECK) {
+        // z = round(sigmoid(logit)), masked to 0.5 beyond the frame's bit budget (bvrnn.py:191-196)
+        float code[8];
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool active = !fr.var_bit || (pf.budget > (float)(col0 + i));
+            const bool bit = active && (sigmoidf_(v[i]) > 0.5f);
+            code[i] = active ? (bit ? 1.f : 0.f) : 0.5f;
+            if (bit) word |= 1u << i;
+        }
+        store_img8(op.out_img, m_tile, op.out_kchunks, row, col0, code, true);   // {0, .5, 1} are exact in bf16
+        const size_t o = ((size_t)m * fr.T + t) * fr.Z + col0;
+        store8(fr.codes + o, code);
+        if (fr.logits) store8(fr.logits + o, v);
+        if (fr.packed) reinterpret_cast<unsigned char*>(fr.packed)[((size_t)m * fr.T + t) * 8 + (col0 >> 3)] = (unsigned char)word;
+        return;
+    }
+    if (op.act) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = elu_fast(v[i]);
+    }
+    if (op.kind == KIND_MEL) {
+        if (fr.mel_out) {
+            float* mo = fr.mel_out + ((size_t)m * fr.T + t) * fr.X;
+            if (col0 + 8 <= fr.X) store8(mo + col0, v);
+            else
+                for (int i = 0; i < 8; ++i)
+                    if (col0 + i < fr.X) mo[col0 + i] = v[i];
+        }
+        return;
+    }
+    if (op.out_img && col0 < op.N) store_img8(op.out_img, m_tile, op.out_kchunks, row, col0, v, false);
+    if (op.out_f && col0 < op.N) store8(op.out_f + (size_t)m * op.ldo + col0, v);
+}
+// Reduce-scatter of a 128 x 64 partial tile with two threads per row: acc = this thread's 8 columns of each of the four
+// quarters (quarter p at acc[8 p]); staging quads 2 hf, 2 hf + 1 of every sender belong to column half hf.
+__device__ __forceinline__ void exchange8(const float* acc, int rank, int hf, int row, uint32_t stg_send, uint32_t stg_full_bar, float* own) {
+#pragma unroll
+    for (int p = 0; p < CLUSTER; ++p) {
+        if (p == rank) continue;
+        const int ss = rank < p ? rank : rank - 1;
+        const uint32_t dst = map_to_cta(stg_send + ss * STG_SENDER_BYTES + (2 * hf) * 2048 + row * 16, (uint32_t)p);
+        const uint32_t bar = map_to_cta(stg_full_bar, (uint32_t)p);
+        st_async_f4(dst, bar, acc[8 * p], acc[8 * p + 1], acc[8 * p + 2], acc[8 * p + 3]);
+        st_async_f4(dst + 2048, bar, acc[8 * p + 4], acc[8 * p + 5], acc[8 * p + 6], acc[8 * p + 7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) own[i] = rank == 0 ? acc[i] : rank == 1 ? acc[8 + i] : rank == 2 ? acc[16 + i] : acc[24 + i];
+}
+// sum the four K quarters in fixed order 0,1,2,3 (bit-reproducible)
+__device__ __forceinline__ void reduce_parts8(const float* own, int rank, int hf, int row, const unsigned char* stg_recv, float* v) {
+#pragma unroll
+    for (int p = 0; p < CLUSTER; ++p) {
+        float part[8];
+        if (p == rank) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part[i] = own[i];
+        } else {
+            const int ss = p < rank ? p : p - 1;
+            const unsigned char* src = stg_recv + ss * STG_SENDER_BYTES + (2 * hf) * 2048 + row * 16;
+            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 2048);
+            part[0] = a.x; part[1] = a.y; part[2] = a.z; part[3] = a.w; part[4] = b.x; part[5] = b.y; part[6] = b.z; part[7] = b.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (p == 0) ? part[i] : v[i] + part[i];
+    }
+}
+
 // Per-CTA schedule, built once in shared memory so that no role chases pointers through L2 inside the time loop
 // (the cluster- and gpu-scope fences of the protocol invalidate L1 all the time).
 constexpr int MAX_MY_ENTRIES = 320;
@@ -473,10 +596,10 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     if (tid == 0) {
         for (int i = 0; i < A_SLOTS; ++i) mbar_init(&bars.fullA[i], 1);
         for (int i = 0; i < W_SLOTS; ++i) { mbar_init(&bars.fullW[i], 1); mbar_init(&bars.emptyW[i], 1); }
-        for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&bars.accFull[i], 1); mbar_init(&bars.accEmpty[i], 4); }
+        for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&bars.accFull[i], 1); mbar_init(&bars.accEmpty[i], 8); }
         mbar_init(&bars.aFree, 1);
         mbar_init(&bars.stgFull, 1);
-        mbar_init(&bars.stgEmpty, 4 * (CLUSTER - 1));
+        mbar_init(&bars.stgEmpty, 8 * (CLUSTER - 1));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         if ((smem_u32(smem_dyn) & 1023u) != 0) atomicCAS(abort_flag, 0, 90);   // SWIZZLE_128B operands need 1 KiB alignment
         // this CTA's schedule
@@ -642,10 +765,16 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
         }
     } else if (warp >= 4) {
         // =========================== epilogue warps ===========================
-        const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
-        const int row = quad * 32 + lane;              // row of the m-tile this thread owns
+        // 8 warps: warp % 4 = TMEM lane quadrant (rows 32 q .. 32 q + 31), hf = (warp - 4) / 4 = column half.  A 64-wide
+        // tile is finished by two threads per row (8 of the 16 columns this CTA owns after the reduce-scatter each); the
+        // 48-wide GRU tiles keep one thread per row (all three gates of 4 units), the hf = 1 warps only keep the barriers
+        // in step.
+        const int quad = warp & 3, hf = (warp - 4) >> 2;
+        const int row = quad * 32 + lane;              // row of the m-tile this thread works on
         const int m = m_tile * TILE_M + row;
         const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+        const uint32_t stg_send = smem_base + SMEM_STG;
+        const unsigned char* stg_recv = smem_gen + SMEM_STG;
         uint32_t accIt = 0, sIt = 0;
         bool dead = false;
         for (int t = 0; t < T && !dead; ++t) {
@@ -655,44 +784,74 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     const uint32_t e = ctl.ent[pl.e_off + j];
                     const Op& op = ctl.ops[e >> 8];
                     const int nt = (int)(e & 0xFF);
-                    const int qc = op.bn >> 2;         // columns per CTA after the reduce-scatter: 16 or 12
-                    const int col0 = pl.split ? nt * op.bn + qc * rank : nt * op.bn;
-                    const int u0 = nt * 16 + 4 * rank; // GRU: first of this thread's 4 hidden units
-                    Prefetch pf;
-                    prefetch_epilogue(op, fr, t, m, col0, u0, pf);
                     const int slot = accIt % ACC_SLOTS, round = accIt / ACC_SLOTS;
-                    if (!mbar_wait<false>(&bars.accFull[slot], round & 1, abort_flag, 31)) { dead = true; break; }
                     ++accIt;
+                    const uint32_t taddr = t_lane + slot * ACC_COLS;
+                    if (op.kind == KIND_GRU) {
+                        // ---- 48-wide tile: thread = row, 12 columns = r, z, n of 4 hidden units ----
+                        const int col0 = nt * 48 + 12 * rank, u0 = nt * 16 + 4 * rank;
+                        Prefetch pf;
+                        if (hf == 0) prefetch_epilogue(op, fr, t, m, col0, u0, pf);
+                        if (!mbar_wait<false>(&bars.accFull[slot], round & 1, abort_flag, 31)) { dead = true; break; }
+                        tc_fence_after();
+                        const int sr = sIt;
+                        ++sIt;
+                        float v[16];
+                        if (hf == 0) {
+                            float acc[64], own[16];
+                            tmem_ld64(taddr, acc);
+                            tc_fence_before();
+                            if (sr >= 1 && !mbar_wait<false>(&bars.stgEmpty, (sr - 1) & 1, abort_flag, 32)) { dead = true; break; }
+                            if (tid == 128) mbar_expect_tx(&bars.stgFull, (uint32_t)((CLUSTER - 1) * TILE_M * 12 * 4));
+                            exchange<12>(acc, rank, row, stg_send, smem_u32(&bars.stgFull), own);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
+                            if (!mbar_wait<false>(&bars.stgFull, sr & 1, abort_flag, 33)) { dead = true; break; }
+                            reduce_parts<12>(own, rank, row, stg_recv, v);
+                        } else {
+                            if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
+                            if (sr >= 1 && !mbar_wait<false>(&bars.stgEmpty, (sr - 1) & 1, abort_flag, 32)) { dead = true; break; }
+                            if (!mbar_wait<false>(&bars.stgFull, sr & 1, abort_flag, 33)) { dead = true; break; }
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+#pragma unroll
+                            for (int p = 0; p < CLUSTER; ++p)
+                                if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)p));
+                        }
+                        if (hf == 0) finalize_gru(fr, t, m, row, m_tile, u0, v, pf);
+                        continue;
+                    }
+                    // ---- 64-wide split tile (or 16-wide full-K tile): two threads per row, 8 columns each ----
+                    const int col0 = pl.split ? nt * 64 + 16 * rank + 8 * hf : nt * 16 + 8 * hf;
+                    Prefetch8 pf;
+                    prefetch8(op, fr, t, m, col0, pf);
+                    if (!mbar_wait<false>(&bars.accFull[slot], round & 1, abort_flag, 31)) { dead = true; break; }
                     if (tid == 128 && j == 0) BVC_TRACE(8);
                     if (tid == 128 && j == pl.n - 1) BVC_TRACE(9);
                     tc_fence_after();
-                    const uint32_t taddr = t_lane + slot * ACC_COLS;
-                    float v[16];
+                    float v[8];
                     if (pl.split) {
-                        // One staging buffer: the epilogue handles one tile at a time anyway, and the peers run the same
-                        // schedule, so "all peers have read tile s - 1" is already true when tile s is ready to be sent.
                         const int sr = sIt;
                         ++sIt;
-                        float acc[64], own[16];
-                        tmem_ld64(taddr, acc);
+                        float acc[32], own[8];
+#pragma unroll
+                        for (int p = 0; p < CLUSTER; ++p) tmem_ld8(taddr + 16 * p + 8 * hf, acc + 8 * p);
+                        tmem_ld_wait();
                         tc_fence_before();
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(10);
                         // my staging slot at every peer is free once all peers have read the previous tile
                         if (sr >= 1 && !mbar_wait<false>(&bars.stgEmpty, (sr - 1) & 1, abort_flag, 32)) { dead = true; break; }
-                        const uint32_t stg_send = smem_base + SMEM_STG;
-                        const unsigned char* stg_recv = smem_gen + SMEM_STG;
-                        // arm my own staging barrier for the 3 x 128 x qc floats the peers will store (st.async complete_tx)
-                        if (tid == 128) mbar_expect_tx(&bars.stgFull, (uint32_t)((CLUSTER - 1) * TILE_M * qc * 4));
-                        if (qc == 16) exchange<16>(acc, rank, row, stg_send, smem_u32(&bars.stgFull), own);
-                        else exchange<12>(acc, rank, row, stg_send, smem_u32(&bars.stgFull), own);
+                        // arm my own staging barrier for the 3 x 128 x 16 floats the peers will store (st.async complete_tx)
+                        if (tid == 128) mbar_expect_tx(&bars.stgFull, (uint32_t)((CLUSTER - 1) * TILE_M * 16 * 4));
+                        exchange8(acc, rank, hf, row, stg_send, smem_u32(&bars.stgFull), own);
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(0);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(11);
                         if (!mbar_wait<false>(&bars.stgFull, sr & 1, abort_flag, 33)) { dead = true; break; }
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(14);
-                        if (qc == 16) reduce_parts<16>(own, rank, row, stg_recv, v);
-                        else reduce_parts<12>(own, rank, row, stg_recv, v);
+                        reduce_parts8(own, rank, hf, row, stg_recv, v);
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(15);
                         __syncwarp();
                         if (lane == 0) {
@@ -702,27 +861,27 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         }
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(1);
                     } else {
-                        tmem_ld16(taddr, v);
+                        tmem_ld8(taddr + 8 * hf, v);
+                        tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
                     }
-                    if (op.kind == KIND_GRU) finalize_gru(fr, t, m, row, m_tile, u0, v, pf);
-                    else finalize16(op, fr, t, m, row, m_tile, col0, v, pf);
+                    finalize8(op, fr, t, m, row, m_tile, col0, v, pf);
                 }
                 // ---- end of phase: publish this CTA's outputs to the m-tile's barrier domain ----
                 if (tid == 128) BVC_TRACE(12);
                 // The outputs are read by other CTAs' bulk copies (async proxy).  The release below is cumulative over the
                 // barrier (the CUTLASS semaphore pattern), and the consumer's copy thread issues fence.proxy.async after its
                 // acquire, before the bulk copies.  A writer-side fence.proxy.async here would be a MEMBAR.ALL.GPU in each of
-                // the 128 epilogue threads on the critical path of every phase.
+                // the epilogue threads on the critical path of every phase.
                 if (dbg_flags & 32) fence_proxy_async_all();
-                {   // barrier over the 4 epilogue warps; a failed wait anywhere retires all of them together
+                {   // barrier over the 8 epilogue warps; a failed wait anywhere retires all of them together
                     uint32_t any;
                     asm volatile(
                         "{\n\t.reg .pred p, q;\n\t"
                         "setp.ne.u32 q, %1, 0;\n\t"
-                        "bar.red.or.pred p, 1, 128, q;\n\t"
+                        "bar.red.or.pred p, 1, 256, q;\n\t"
                         "selp.u32 %0, 1, 0, p;\n\t}\n"
                         : "=r"(any)
                         : "r"((uint32_t)dead)
