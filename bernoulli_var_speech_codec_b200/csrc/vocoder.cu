@@ -568,30 +568,34 @@ __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
 //                   works on the other two.
 //   tile prologue   input tile (mean of the producer's partials) -> ConvTranspose1d with mma.sync (3 % of the MACs) ->
 //                   x of the three resblocks (tcgen05.st) and their first conv inputs
-constexpr int UM_TT = 128;
+constexpr int UM_ROWS = 128;                                    // rows of one MMA (UMMA M)
 constexpr int UM_PADR = 8;
 constexpr int UM_WSLOTS = 3;
 constexpr int UM_WSLOT_BYTES = 16384;
 __host__ __device__ constexpr int um_K(int c) { return c == 0 ? 11 : c == 1 ? 7 : 3; }
-__host__ __device__ constexpr int um_R1(int c) { return (um_K(c) - 1) * 5 + UM_TT + UM_PADR; }
-__host__ __device__ constexpr int um_R2(int c) { return (um_K(c) - 1) + UM_TT + UM_PADR; }
+__host__ __device__ constexpr int um_R1(int c, int TT) { return (um_K(c) - 1) * 5 + TT + UM_PADR; }
+__host__ __device__ constexpr int um_R2(int c, int TT) { return (um_K(c) - 1) + TT + UM_PADR; }
 
-template <int C, int U>
+// MT = 128-row MMA tiles per CTA tile: a conv job issues MT MMAs per k16 step and term, and its epilogue covers 128 MT
+// rows with MT times the threads, so the per-job latency (~1 us: TMEM read, barrier, SnakeBeta, proxy fence, mbarrier
+// round trips) is spread over more samples.  C = 32 is MMA-bound already at MT = 1; C = 16 needs MT = 2.
+template <int C, int U, int MT>
 struct UmLayout {
+    static constexpr int TT = UM_ROWS * MT;
     static constexpr int G = C / 8, N = C < 16 ? 16 : C, CIN = 2 * C;
     static constexpr int PWI = RowLayout<CIN>::PW;
-    static constexpr int NJ = UM_TT / U + 1;
+    static constexpr int NJ = TT / U + 1;
     // byte offsets
-    __host__ __device__ static constexpr int a1(int c) { return c == 0 ? 0 : a1(c - 1) + 2 * G * um_R1(c - 1) * 16; }
-    __host__ __device__ static constexpr int a2(int c) { return c == 0 ? a1(3) : a2(c - 1) + 2 * G * um_R2(c - 1) * 16; }
+    __host__ __device__ static constexpr int a1(int c) { return c == 0 ? 0 : a1(c - 1) + 2 * G * um_R1(c - 1, TT) * 16; }
+    __host__ __device__ static constexpr int a2(int c) { return c == 0 ? a1(3) : a2(c - 1) + 2 * G * um_R2(c - 1, TT) * 16; }
     // saved contexts: per chain [layer][part][group][row][16 B]; layer l of the dilated conv has (K-1) d_l rows
     __host__ __device__ static constexpr int c1(int c) { return c == 0 ? a2(3) : c1(c - 1) + 2 * G * (um_K(c - 1) - 1) * 9 * 16; }
     __host__ __device__ static constexpr int c2(int c) { return c == 0 ? c1(3) : c2(c - 1) + 2 * G * (um_K(c - 1) - 1) * 3 * 16; }
     static constexpr int wring = (c2(3) + 1023) / 1024 * 1024;
     static constexpr int x0 = wring + UM_WSLOTS * UM_WSLOT_BYTES;          // fp32 [128][C + 4]
-    static constexpr int xin = x0 + UM_TT * (C + 4) * 4;                   // hi, lo [NJ + 16][PWI] words
+    static constexpr int xin = x0 + TT * (C + 4) * 4;                   // hi, lo [NJ + 16][PWI] words
     static constexpr int total = xin + 2 * (NJ + 16) * PWI * 4;
-    static constexpr int tmem_cols = 6 * N <= 128 ? 128 : 256;
+    static constexpr int tmem_cols = 6 * N * MT <= 128 ? 128 : 6 * N * MT <= 256 ? 256 : 512;
 };
 
 struct UmmaStageArgs {
@@ -716,12 +720,13 @@ __device__ __forceinline__ void um_store8(unsigned char* part_hi, int part_strid
     *reinterpret_cast<uint4*>(part_hi + part_stride + (size_t)offset16 * 16) = l;
 }
 
-template <int C, int U>
-__global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(UmmaStageArgs a) {
-    using L = UmLayout<C, U>;
+template <int C, int U, int MT>
+__global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel(UmmaStageArgs a) {
+    using L = UmLayout<C, U, MT>;
+    constexpr int UM_TT = L::TT;
     constexpr int G = L::G, N = L::N, CIN = L::CIN, PWI = L::PWI, NJ = L::NJ, PX = C + 4;
     constexpr int HALO = 12 * (11 - 1);
-    constexpr int UM_THREADS = 128 + 128 * G;     // warps 0-3: MMA issue, weight stream, 2 idle; then G epilogue groups of 4 warps
+    constexpr int UM_THREADS = 128 + 128 * G * MT;     // warps 0-3: MMA issue, weight stream, 2 idle; then G epilogue groups of 4 warps
     extern __shared__ __align__(1024) unsigned char um_smem[];
     __shared__ __align__(8) uint64_t a_ready[3], d_ready[3], w_full[UM_WSLOTS], w_empty[UM_WSLOTS];
     __shared__ uint32_t tmem_slot;
@@ -742,7 +747,7 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(Umma
     for (int i = tid; i < L::wring / 16; i += UM_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&a_ready[i])), "r"(4 * G));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&a_ready[i])), "r"(4 * G * MT));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&d_ready[i])), "r"(1));
         }
         for (int i = 0; i < UM_WSLOTS; ++i) {
@@ -783,7 +788,7 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(Umma
         }
     } else if (warp == 0) {
         // =========================== MMA issue ===========================
-        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UM_TT >> 4) << 24);
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
         constexpr int SPC = UM_WSLOT_BYTES / (N * 64);       // k16 steps per weight chunk
         uint32_t wit = 0;
         uint32_t jobs_done[3] = {0, 0, 0};                    // per chain: selects the parity of a_ready
@@ -801,7 +806,7 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(Umma
                 const int lead = jb.conv2 ? (K - 1) : (K - 1) * 5;
                 const uint32_t abase = sm_a + (jb.conv2 ? (c == 0 ? L::a2(0) : c == 1 ? L::a2(1) : L::a2(2))
                                                         : (c == 0 ? L::a1(0) : c == 1 ? L::a1(1) : L::a1(2)));
-                const uint32_t d_tmem = tmem + (uint32_t)(c * 2 * N + (jb.conv2 ? 0 : N));
+                const uint32_t d_tmem = tmem + (uint32_t)(c * 2 * N + (jb.conv2 ? 0 : N));     // row tile mt: + mt * 6 N columns
                 // Descriptors advance by plain additions on their 16-byte-unit address field:
                 //   C >= 16: step (tap, channel pair gq): +d rows per tap, +2 R rows per channel pair (two 8-channel groups)
                 //   C == 8 : step s covers taps 2s, 2s+1: +2 d rows per step, LBO = d rows
@@ -821,11 +826,16 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(Umma
                         uint64_t dwh = um_desc(sm_a + L::wring + slot * UM_WSLOT_BYTES, N * 16);
 #pragma unroll 2
                         for (int s = s0; s < s1; ++s) {
-                            const uint64_t dah = dA0 + (uint64_t)(tap_off16 + gq * (uint32_t)(2 * R));
-                            const uint64_t dal = dah + a_lo16, dwl = dwh + (uint64_t)(N * 2);
-                            um_mma(d_tmem, dal, dwh, idesc, first);
-                            um_mma(d_tmem, dah, dwl, idesc, 1u);
-                            um_mma(d_tmem, dah, dwh, idesc, 1u);
+                            const uint64_t dah0 = dA0 + (uint64_t)(tap_off16 + gq * (uint32_t)(2 * R));
+                            const uint64_t dwl = dwh + (uint64_t)(N * 2);
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {       // the weight step is fetched once per 128-row tile
+                                const uint64_t dah = dah0 + (uint64_t)(mt * UM_ROWS), dal = dah + a_lo16;
+                                const uint32_t dt = d_tmem + (uint32_t)(mt * 6 * N);
+                                um_mma(dt, dal, dwh, idesc, first);
+                                um_mma(dt, dah, dwl, idesc, 1u);
+                                um_mma(dt, dah, dwh, idesc, 1u);
+                            }
                             first = 1u;
                             dwh += (uint64_t)(N * 4);
                             if (SPT == 1 || ++gq == SPT) { gq = 0; tap_off16 += step_tap16; }
@@ -855,9 +865,11 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(Umma
         // =========================== epilogue (thread = time row x 8-channel group) ===========================
         // G groups of 4 warps; group g owns channels 8g .. 8g+7 of all 128 rows (a warp may only touch the TMEM lane
         // quadrant warp % 4, so each group is one full set of quadrants)
-        constexpr int NE = 128 * G;
-        const int et = tid - 128, g = (warp - 4) >> 2, quad = warp & 3, p = quad * 32 + lane;   // p: tile row = TMEM lane
-        const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+        constexpr int NE = 128 * G * MT;
+        const int et = tid - 128, wg = (warp - 4) >> 2, g = wg % G, mt = wg / G, quad = warp & 3;
+        const int pl = quad * 32 + lane;               // TMEM lane = row of the 128-row MMA tile
+        const int p = mt * UM_ROWS + pl;               // row of the CTA tile
+        const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 6 * N);
         uint32_t* xh = reinterpret_cast<uint32_t*>(sm + L::xin);
         uint32_t* xl = xh + (NJ + 16) * PWI;
         float* x0 = reinterpret_cast<float*>(sm + L::x0);
@@ -941,7 +953,7 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(Umma
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) bup[nt] = __ldg(reinterpret_cast<const float2*>(a.b_up + nt * 8 + 2 * (tid & 3)));
                 const uint32_t xh_a = um_smem_u32(xh), xl_a = um_smem_u32(xl);
-                for (int item = warp - 4; item < U * tiles; item += 4 * G) {
+                for (int item = warp - 4; item < U * tiles; item += 4 * G * MT) {
                     const int r = item / tiles, tl = item - r * tiles;
                     const uint2* wh = a.upf_h + (size_t)r * KC_UP * NT * 32;
                     const uint2* wl = a.upf_l + (size_t)r * KC_UP * NT * 32;
@@ -952,7 +964,7 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(Umma
             }
             // contexts of the first dilated convs (layer 0) in front of the tiles
 #pragma unroll
-            for (int c = 0; c < 3; ++c) restore(a1_off(c), um_R1(c), (um_K(c) - 1) * 5, c1_off(c, 0), (um_K(c) - 1) * 1);
+            for (int c = 0; c < 3; ++c) restore(a1_off(c), um_R1(c, UM_TT), (um_K(c) - 1) * 5, c1_off(c, 0), (um_K(c) - 1) * 1);
             epi_bar();
             // ---- x of the three resblocks = x0 (TMEM) and their first conv inputs ----
             float xr[8];
@@ -968,7 +980,7 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(Umma
                 load8(a.ieb[c][0], ieb);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) y[i] = snake_fast(xr[i], ea[i], ieb[i]);
-                write_rows(a1_off(c), um_R1(c), (um_K(c) - 1) * 5, y, c1_off(c, 0), (um_K(c) - 1) * 1);
+                write_rows(a1_off(c), um_R1(c, UM_TT), (um_K(c) - 1) * 5, y, c1_off(c, 0), (um_K(c) - 1) * 1);
                 asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
                 publish(c);
             }
@@ -1037,12 +1049,13 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8), 1) stage_umma_kernel(Umma
     }
 }
 
-template <int C, int U>
+template <int C, int U, int MT>
 int launch_stage_umma(const UmmaStageArgs& a, int B, cudaStream_t stream) {
-    using L = UmLayout<C, U>;
+    using L = UmLayout<C, U, MT>;
+    constexpr int UM_TT = L::TT;
     static int sms = 0;
     if (!sms) {
-        BVC_CUDA(cudaFuncSetAttribute(stage_umma_kernel<C, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
+        BVC_CUDA(cudaFuncSetAttribute(stage_umma_kernel<C, U, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
         int dev = 0;
         BVC_CUDA(cudaGetDevice(&dev));
         BVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1055,7 +1068,7 @@ int launch_stage_umma(const UmmaStageArgs& a, int B, cudaStream_t stream) {
     if (ranges < 1) ranges = 1;
     const int tiles_per = (tiles_total + ranges - 1) / ranges;
     ranges = (tiles_total + tiles_per - 1) / tiles_per;
-    stage_umma_kernel<C, U><<<dim3(ranges, B), 128 + 128 * L::G, L::total, stream>>>(a);
+    stage_umma_kernel<C, U, MT><<<dim3(ranges, B), 128 + 128 * L::G * MT, L::total, stream>>>(a);
     BVC_CHECK_LAUNCH();
     return BVC_OK;
 }
@@ -1218,7 +1231,7 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
     // Stages that run on the tcgen05 kernel (bit i = stage i).  Its MMAs fetch the 128 x 16 activation operand from
     // shared memory for every instruction (~64 clk measured), so with N = C_out it sustains ~40 C_out MAC/clk: twice the
     // mma.sync kernel at C = 32, on par at 16, behind at 8 where the per-job epilogue latency dominates.  Default: stage 1.
-    static const int umma_mask = getenv("BVC_VOC_UMMA") ? atoi(getenv("BVC_VOC_UMMA")) : 0x2;
+    static const int umma_mask = getenv("BVC_VOC_UMMA") ? atoi(getenv("BVC_VOC_UMMA")) : 0x6;
     bool single[4] = {false, false, false, false};     // stage i wrote one tensor (the mean) instead of three partials
     for (int i = 0; i < 4; ++i) {
         if (precision >= 1 && ((umma_mask >> i) & 1) && i >= 1 && w.umma[i].ready) {
@@ -1248,9 +1261,9 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
             }
             int rc;
             switch (vb.C[i + 1]) {
-                case 32: rc = launch_stage_umma<32, 8>(ua, B, stream); break;
-                case 16: rc = launch_stage_umma<16, 2>(ua, B, stream); break;
-                default: rc = launch_stage_umma<8, 2>(ua, B, stream); break;
+                case 32: rc = launch_stage_umma<32, 8, 1>(ua, B, stream); break;
+                case 16: rc = launch_stage_umma<16, 2, 2>(ua, B, stream); break;
+                default: rc = launch_stage_umma<8, 2, 4>(ua, B, stream); break;
             }
             if (rc != BVC_OK) return rc;
             if (tracing) {   // per job: MMA warp got the operand / issued all MMAs, epilogue saw the result / finished
