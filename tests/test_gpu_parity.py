@@ -221,3 +221,34 @@ def test_packed_wire_format_round_trip(model_var, model_fix, oracle_var):
     # fixed-rate model: every bit is active whatever the budget says
     pk, bits = model_fix.encode_packed(x, 3000)
     assert torch.equal(model_fix._engine.unpack_codes(pk, None, bits), model_fix.encode(x, 3000))
+
+
+def test_streaming_equals_offline(model_var):
+    """Chunk-by-chunk encode / decode with carried state (streaming.py) reproduces the offline calls exactly."""
+    from bernoulli_var_speech_codec_b200.streaming import StreamingDecoder, StreamingEncoder
+    B, L = 3, 256 * 61 + 100
+    x = _noise(B, L, 91).to(model_var.device)
+    codes_off = model_var.encode(x, 3000)
+    wav_off = model_var.decode(codes_off, L)
+    g = torch.Generator().manual_seed(3)
+    for chunk_sizes in ([256] * 70, [1000, 37, 4096, 5, 700, 2048] * 4):      # hop-sized real-time feed; ragged chunks
+        enc, dec = StreamingEncoder(model_var, 3000), StreamingDecoder(model_var)
+        codes_s, wav_s, pos = [], [], 0
+        for n in chunk_sizes:
+            if pos >= L:
+                break
+            c = enc.push(x[:, pos:pos + n])
+            pos = min(pos + n, L)
+            if c is not None:
+                codes_s.append(c)
+                wav_s.append(dec.push(c))
+        c = enc.flush()
+        if c is not None:
+            codes_s.append(c)
+            wav_s.append(dec.push(c))
+        codes_s = torch.cat(codes_s, 1)
+        assert codes_s.shape == codes_off.shape and torch.equal(codes_s, codes_off)
+        tail = dec.flush(L - 256 * codes_off.shape[1])
+        wav_cat = torch.cat(wav_s + ([tail] if tail is not None else []), 1)
+        assert wav_cat.shape == wav_off.shape
+        assert (wav_cat - wav_off).abs().max() <= 1e-5
