@@ -650,14 +650,13 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
         const int Cs = (int)(C0 >> (i + 1));
         const bool cfg_ok = w.n_kernels == 3 && c.voc_res_kernels[0] == 3 && c.voc_res_kernels[1] == 7 && c.voc_res_kernels[2] == 11 &&
                             c.voc_res_dilations[0] == 1 && c.voc_res_dilations[1] == 3 && c.voc_res_dilations[2] == 5;
-        if (!cfg_ok || Cs > 32 || Cs < 8) continue;
-        const int N = Cs < 16 ? 16 : Cs, SPC = 16384 / (N * 64);
+        if (!cfg_ok || Cs > 64 || Cs < 8) continue;
+        const int N = Cs < 16 ? 16 : Cs;
         std::vector<unsigned char> stream;
-        int n_jobs = 0, n_chunks = 0;
-        bool fits = true;
-        for (int l = 0; l < 3 && fits; ++l)
-            for (int conv2 = 0; conv2 < 2 && fits; ++conv2)
-                for (int cc = 0; cc < 3 && fits; ++cc) {
+        int n_jobs = 0;
+        for (int l = 0; l < 3; ++l)
+            for (int conv2 = 0; conv2 < 2; ++conv2)
+                for (int cc = 0; cc < 3; ++cc) {
                     const int j = 2 - cc;                       // chain 0 = k 11, 1 = k 7, 2 = k 3
                     const int K = c.voc_res_kernels[j];
                     const std::string rb = "resblocks." + std::to_string(i * 3 + j);
@@ -666,15 +665,10 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
                     UmmaJob& jb = um.jobs[n_jobs++];
                     jb.chain = (short)cc; jb.layer = (short)l; jb.conv2 = (short)conv2; jb.K = (short)K;
                     jb.d = (short)(conv2 ? 1 : c.voc_res_dilations[l]);
-                    jb.steps = (short)steps; jb.chunk0 = (short)n_chunks;
-                    for (int s0 = 0; s0 < steps; s0 += SPC) {
-                        if (n_chunks >= 48) { fits = false; break; }
-                        const int s1 = std::min(steps, s0 + SPC);
-                        um.chunk_off[n_chunks] = (int)stream.size();
-                        um.chunk_bytes[n_chunks] = (s1 - s0) * N * 64;
-                        ++n_chunks;
-                        for (int st = s0; st < s1; ++st) {
-                            std::vector<uint16_t> blk((size_t)N * 32, 0);   // [part][group][N][8]
+                    jb.steps = (short)steps; jb.off = (int)stream.size();
+                    {
+                        for (int st = 0; st < steps; ++st) {
+                            std::vector<uint16_t> blk((size_t)N * 32, 0);   // [k group][hi | lo][N][8]
                             for (int gq = 0; gq < 2; ++gq)
                                 for (int n = 0; n < Cs; ++n)
                                     for (int e = 0; e < 8; ++e) {
@@ -683,17 +677,14 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
                                         else { tap = 2 * st + gq; ci = e; }
                                         const float v = tap < K ? f[((size_t)n * Cs + ci) * K + tap] : 0.f;
                                         const uint16_t vh = f2bf(v), vl = f2bf(v - bf2f(vh));
-                                        blk[((size_t)(0 * 2 + gq) * N + n) * 8 + e] = vh;
-                                        blk[((size_t)(1 * 2 + gq) * N + n) * 8 + e] = vl;
+                                        blk[((size_t)(gq * 2 + 0) * N + n) * 8 + e] = vh;
+                                        blk[((size_t)(gq * 2 + 1) * N + n) * 8 + e] = vl;
                                     }
                             const unsigned char* bp = reinterpret_cast<const unsigned char*>(blk.data());
                             stream.insert(stream.end(), bp, bp + blk.size() * 2);
                         }
                     }
-                    jb.nchunks = (short)(n_chunks - jb.chunk0);
                 }
-        if (!fits) continue;
-        um.n_chunks = n_chunks;
         um.wstream = dev_upload(h, stream);
         ok = ok && um.wstream;
         for (int cc = 0; cc < 3; ++cc) {

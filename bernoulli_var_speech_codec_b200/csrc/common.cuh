@@ -178,14 +178,12 @@ struct AmpBlockWeights {
 // Stage on the 5th-gen tensor cores (vocoder.cu, stage_umma_kernel): one tile = 18 convolution "jobs" (3 resblocks x
 // 3 layers x 2 convs) whose weights are streamed in MMA issue order as chunks of <= 16 KiB
 struct UmmaJob {
-    short chain, layer, conv2, K, d, steps, chunk0, nchunks;
+    short chain, layer, conv2, K, d, steps;
+    int off;                                  // byte offset of the job's weight chunks in the stream (16 KB each, the last one shorter)
 };
 struct UmmaStageWeights {
     bool ready = false;
     const unsigned char* wstream = nullptr;   // all chunks of one tile, concatenated
-    int n_chunks = 0;
-    int chunk_off[48];
-    int chunk_bytes[48];
     UmmaJob jobs[18];
     const float* b1[3][3];                    // [chain][layer] bias of the dilated conv
     const float* bsum[3][3];                  // [chain][layer] sum of the second convs' biases of layers 0..layer
@@ -207,6 +205,7 @@ struct VocoderWeights {
 struct VocoderBuffers {       // views into the workspace, valid after the last vocoder_forward
     float* mel_pad = nullptr; // [B, T+6, n_mels]
     float* pre = nullptr;     // [B, T+6, c0] channel-last (rows t >= T of each utterance are scratch)
+    float* x0 = nullptr;      // [B, n, C] output of a stage's transposed convolution (tcgen05 stage kernels; reused by every stage)
     float* part[4][3];        // per stage, per resblock: [B, n, C] channel-last
     int64_t n[5];             // n[0] = T, n[i+1] = length after stage i
     int C[5];

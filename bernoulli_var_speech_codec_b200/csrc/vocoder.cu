@@ -21,6 +21,7 @@
 //                M = time, N = C_out, K = taps x C_in.  Conv inputs live in shared memory as split
 //                bf16 (hi, lo) rows [time][C]; a tap is a row offset of the A fragment, so no im2col
 //                copy exists.  x.w ~= x_hi.w_hi + x_hi.w_lo + x_lo.w_hi.  The residual stream stays fp32.
+#include <algorithm>
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -576,39 +577,53 @@ __host__ __device__ constexpr int um_K(int c) { return c == 0 ? 11 : c == 1 ? 7 
 __host__ __device__ constexpr int um_R1(int c, int TT) { return (um_K(c) - 1) * 5 + TT + UM_PADR; }
 __host__ __device__ constexpr int um_R2(int c, int TT) { return (um_K(c) - 1) + TT + UM_PADR; }
 
-// MT = 128-row MMA tiles per CTA tile: a conv job issues MT MMAs per k16 step and term, and its epilogue covers 128 MT
-// rows with MT times the threads, so the per-job latency (~1 us: TMEM read, barrier, SnakeBeta, proxy fence, mbarrier
-// round trips) is spread over more samples.  C = 32 is MMA-bound already at MT = 1; C = 16 needs MT = 2.
-template <int C, int U, int MT>
+// MT  = 128-row MMA tiles per CTA tile: a conv job issues MT MMAs per k16 step and term, and its epilogue covers 128 MT
+//       rows with MT times the threads, so the per-job latency (~1 us: TMEM read, barrier, SnakeBeta, proxy fence,
+//       mbarrier round trips) is spread over more samples.  C = 32 is MMA-bound already at MT = 1; C = 16 needs MT = 2.
+// NCH = resblocks ("chains") per CTA: 3 = all of them, interleaved (their mean is written); 1 = the resblock blockIdx.z
+//       (C = 64: three chains do not fit in shared memory; each CTA then writes its resblock's partial tensor).
+template <int C, int U, int MT, int NCH>
 struct UmLayout {
     static constexpr int TT = UM_ROWS * MT;
     static constexpr int G = C / 8, N = C < 16 ? 16 : C, CIN = 2 * C;
-    static constexpr int PWI = RowLayout<CIN>::PW;
-    static constexpr int NJ = TT / U + 1;
-    // byte offsets
+    static constexpr int CPT = C > 32 ? 16 : 8;                 // channels per epilogue thread
+    static constexpr int GE = C / CPT;                           // epilogue warp groups per 128-row tile
+    // byte offsets; with NCH = 1 the single chain is sized for the largest kernel (local index 0 = k 11)
     __host__ __device__ static constexpr int a1(int c) { return c == 0 ? 0 : a1(c - 1) + 2 * G * um_R1(c - 1, TT) * 16; }
-    __host__ __device__ static constexpr int a2(int c) { return c == 0 ? a1(3) : a2(c - 1) + 2 * G * um_R2(c - 1, TT) * 16; }
+    __host__ __device__ static constexpr int a2(int c) { return c == 0 ? a1(NCH) : a2(c - 1) + 2 * G * um_R2(c - 1, TT) * 16; }
     // saved contexts: per chain [layer][part][group][row][16 B]; layer l of the dilated conv has (K-1) d_l rows
-    __host__ __device__ static constexpr int c1(int c) { return c == 0 ? a2(3) : c1(c - 1) + 2 * G * (um_K(c - 1) - 1) * 9 * 16; }
-    __host__ __device__ static constexpr int c2(int c) { return c == 0 ? c1(3) : c2(c - 1) + 2 * G * (um_K(c - 1) - 1) * 3 * 16; }
-    static constexpr int wring = (c2(3) + 1023) / 1024 * 1024;
-    static constexpr int x0 = wring + UM_WSLOTS * UM_WSLOT_BYTES;          // fp32 [128][C + 4]
-    static constexpr int xin = x0 + TT * (C + 4) * 4;                   // hi, lo [NJ + 16][PWI] words
-    static constexpr int total = xin + 2 * (NJ + 16) * PWI * 4;
-    static constexpr int tmem_cols = 6 * N * MT <= 128 ? 128 : 6 * N * MT <= 256 ? 256 : 512;
+    __host__ __device__ static constexpr int c1(int c) { return c == 0 ? a2(NCH) : c1(c - 1) + 2 * G * (um_K(c - 1) - 1) * 9 * 16; }
+    __host__ __device__ static constexpr int c2(int c) { return c == 0 ? c1(NCH) : c2(c - 1) + 2 * G * (um_K(c - 1) - 1) * 3 * 16; }
+    static constexpr int wring = (c2(NCH) + 1023) / 1024 * 1024;
+    static constexpr int x0 = wring + UM_WSLOTS * UM_WSLOT_BYTES;          // fp32 [TT][C + 4]: the upsampled tile (bulk-copied)
+    static constexpr int total = x0 + TT * (C + 4) * 4;
+    // TMEM columns per 128-row tile and chain: [x | x aux | D1 | D1 aux], N each.  A product is a_hi [w_hi | w_lo] (one MMA
+    // of width 2 N: main and aux accumulator) + a_lo w_hi (width N): the activation operand, whose fetch from shared
+    // memory bounds these narrow MMAs, is read twice per k16 step instead of three times; the epilogue adds main + aux.
+    static constexpr int tile_cols = 4 * N * NCH;
+    static constexpr int tmem_cols = tile_cols * MT <= 128 ? 128 : tile_cols * MT <= 256 ? 256 : 512;
+    static constexpr int threads = 128 + 128 * GE * MT;
 };
 
-struct UmmaStageArgs {
-    const float* in_p[3];
+// The transposed convolution that opens a stage runs as its own kernel (upsample_kernel) and leaves x0 [B, n_out, C] in
+// global memory; the stage kernel bulk-copies its tile of x0 one tile ahead.
+struct UpsampleArgs {
+    const float* in_p[3];       // the producer's partials [B, n_in, 2 C] channel-last (n_parts = 1: a single tensor)
     int n_parts;
     long long in_bstride;
     int n_in, n_out;
     const float* b_up;
-    const uint2* upf_h;
+    const uint2* upf_h;         // per output phase r: fragment-packed 2-tap weights, hi / lo parts
     const uint2* upf_l;
+    float* x0;                  // [B, n_out, C]
+};
+
+struct UmmaStageArgs {
+    const float* x0;            // [B, n_out, C] (+ one tile of readable slack)
+    int n_out;
     const float* ea[3][6];
     const float* ieb[3][6];
-    float* out;                 // [B, n_out, C] channel-last: the mean of the three resblocks
+    float* out[3];              // NCH = 3: out[0] = [B, n_out, C] mean of the resblocks; NCH = 1: out[chain] = its partial
     unsigned long long* trace;  // bring-up: CTA (0,0), tile 2: per job 4 %globaltimer stamps (+ 2 for the tile prologue)
     UmmaStageWeights w;
 };
@@ -641,7 +656,7 @@ __device__ __forceinline__ unsigned long long um_ns() {
 }
 #define UM_TRACE(slot)                                                                         \
     do {                                                                                       \
-        if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && tile == 2) a.trace[slot] = um_ns(); \
+        if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile == 2) a.trace[slot] = um_ns(); \
     } while (0)
 __device__ __forceinline__ void um_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(um_smem_u32(bar)) : "memory");
@@ -720,21 +735,81 @@ __device__ __forceinline__ void um_store8(unsigned char* part_hi, int part_strid
     *reinterpret_cast<uint4*>(part_hi + part_stride + (size_t)offset16 * 16) = l;
 }
 
-template <int C, int U, int MT>
-__global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel(UmmaStageArgs a) {
-    using L = UmLayout<C, U, MT>;
+// ConvTranspose1d(2 C -> C, kernel 2 U, stride U) as U phase convolutions with 2 taps each (mma.sync, split bf16):
+// out[U j + r] = W[r + U] in[j - 1] + W[r] in[j].  A CTA owns (utterance, JT input rows); a warp keeps one phase so
+// that its weight fragments stay in L1 over its row tiles.
+template <int C, int U>
+__global__ void __launch_bounds__(256) upsample_kernel(UpsampleArgs a) {
+    constexpr int CIN = 2 * C, PWI = RowLayout<CIN>::PW, JT = 512 / U, MTU = 2, NT = C / 8, KC_UP = (2 * CIN) / 16;
+    __shared__ __align__(16) uint32_t xh[(JT + 1) * PWI];
+    __shared__ __align__(16) uint32_t xl[(JT + 1) * PWI];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int b = blockIdx.y, j0 = blockIdx.x * JT;
+    const size_t boff = (size_t)b * a.in_bstride;
+    constexpr int V = CIN / 4;
+    for (int i = tid; i < (JT + 1) * V; i += 256) {
+        const int jj = i / V, c4 = i - jj * V;
+        const int j = j0 - 1 + jj;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j >= 0 && j < a.n_in) {
+            const size_t o = boff + (size_t)j * CIN + c4 * 4;
+            v = __ldg(reinterpret_cast<const float4*>(a.in_p[0] + o));
+            if (a.n_parts == 3) {
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.in_p[1] + o));
+                const float4 v2 = __ldg(reinterpret_cast<const float4*>(a.in_p[2] + o));
+                v.x = ((v.x + v1.x) + v2.x) / 3.0f; v.y = ((v.y + v1.y) + v2.y) / 3.0f;
+                v.z = ((v.z + v1.z) + v2.z) / 3.0f; v.w = ((v.w + v1.w) + v2.w) / 3.0f;
+            }
+        }
+        uint32_t h0, l0, h1, l1;
+        split_pair(v.x, v.y, h0, l0);
+        split_pair(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2*>(xh + jj * PWI + c4 * 2) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(xl + jj * PWI + c4 * 2) = make_uint2(l0, l1);
+    }
+    __syncthreads();
+    float2 bup[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) bup[nt] = __ldg(reinterpret_cast<const float2*>(a.b_up + nt * 8 + 2 * (tid & 3)));
+    const uint32_t xh_a = (uint32_t)__cvta_generic_to_shared(xh), xl_a = (uint32_t)__cvta_generic_to_shared(xl);
+    constexpr int RT = JT / (16 * MTU);                 // row tiles per phase
+    float* dst = a.x0 + (size_t)b * a.n_out * C;
+    for (int item = warp; item < U * RT; item += 8) {   // U = 8: phase = warp; U = 2: phase = warp & 1
+        const int r = item % U, tl = item / U;
+        const uint2* wh = a.upf_h + (size_t)r * KC_UP * NT * 32;
+        const uint2* wl = a.upf_l + (size_t)r * KC_UP * NT * 32;
+        mma_rows<CIN, C, 2, MTU>(xh_a, xl_a, 1, wh, wl, 1, tl * 16 * MTU, [&](int row, int nt, int co, float v0, float v1) {
+            const long long t = (long long)U * (j0 + row) + r;
+            if (t < a.n_out) *reinterpret_cast<float2*>(dst + t * C + co) = make_float2(v0 + bup[nt].x, v1 + bup[nt].y);
+        });
+    }
+}
+
+template <int C, int U>
+int launch_upsample(const UpsampleArgs& a, int B, cudaStream_t stream) {
+    constexpr int JT = 512 / U;
+    upsample_kernel<C, U><<<dim3((a.n_in + 1 + JT - 1) / JT, B), 256, 0, stream>>>(a);
+    BVC_CHECK_LAUNCH();
+    return BVC_OK;
+}
+
+template <int C, int U, int MT, int NCH>
+__global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umma_kernel(UmmaStageArgs a) {
+    using L = UmLayout<C, U, MT, NCH>;
     constexpr int UM_TT = L::TT;
-    constexpr int G = L::G, N = L::N, CIN = L::CIN, PWI = L::PWI, NJ = L::NJ, PX = C + 4;
+    constexpr int G = L::G, N = L::N, PX = C + 4, CPT = L::CPT, GE = L::GE;
+    constexpr int S8 = CPT / 8;                        // 8-channel operand groups per epilogue thread
     constexpr int HALO = 12 * (11 - 1);
-    constexpr int UM_THREADS = 128 + 128 * G * MT;     // warps 0-3: MMA issue, weight stream, 2 idle; then G epilogue groups of 4 warps
+    constexpr int UM_THREADS = L::threads;             // warps 0-3: MMA issue, weight stream, 2 idle; then GE MT epilogue groups of 4 warps
     extern __shared__ __align__(1024) unsigned char um_smem[];
-    __shared__ __align__(8) uint64_t a_ready[3], d_ready[3], w_full[UM_WSLOTS], w_empty[UM_WSLOTS];
+    __shared__ __align__(8) uint64_t a_ready[3], d_ready[3], w_full[UM_WSLOTS], w_empty[UM_WSLOTS], x_full, x_empty;
     __shared__ uint32_t tmem_slot;
     unsigned char* sm = um_smem;
     const uint32_t sm_a = um_smem_u32(um_smem);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
+    const int kc0 = NCH == 1 ? (int)blockIdx.z : 0;    // first resblock of this CTA; local chain lc <-> resblock kc0 + lc
     const int tiles_total = (a.n_out + UM_TT - 1) / UM_TT;
     const int tiles_per = (tiles_total + gridDim.x - 1) / gridDim.x;
     const int t_begin = blockIdx.x * tiles_per * UM_TT;
@@ -747,13 +822,15 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
     for (int i = tid; i < L::wring / 16; i += UM_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&a_ready[i])), "r"(4 * G * MT));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&a_ready[i])), "r"(4 * GE * MT));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&d_ready[i])), "r"(1));
         }
         for (int i = 0; i < UM_WSLOTS; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&w_full[i])), "r"(1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&w_empty[i])), "r"(1));
         }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&x_full)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&x_empty)), "r"(4 * GE * MT));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -771,24 +848,47 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
         // =========================== weight stream ===========================
         uint32_t it = 0;
         for (int tile = 0; tile < n_tiles; ++tile) {
-            for (int ch = 0; ch < a.w.n_chunks; ++ch, ++it) {
-                const int slot = it % UM_WSLOTS, round = it / UM_WSLOTS;
-                if (round >= 1) um_wait(&w_empty[slot], (round - 1) & 1);
-                if (um_elect()) {
-                    const uint32_t bytes = (uint32_t)a.w.chunk_bytes[ch];
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(um_smem_u32(&w_full[slot])), "r"(bytes)
-                                 : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                                     sm_a + L::wring + slot * UM_WSLOT_BYTES),
-                                 "l"(a.w.wstream + a.w.chunk_off[ch]), "r"(bytes), "r"(um_smem_u32(&w_full[slot]))
-                                 : "memory");
+#pragma unroll 1
+            for (int ji = 0; ji < 18; ++ji) {
+                const UmmaJob jb = a.w.jobs[ji];
+                if (jb.chain < kc0 || jb.chain >= kc0 + NCH) continue;
+                constexpr int SPCW = UM_WSLOT_BYTES / (N * 64);
+                for (int s0 = 0; s0 < jb.steps; s0 += SPCW, ++it) {
+                    const int slot = it % UM_WSLOTS, round = it / UM_WSLOTS;
+                    if (round >= 1) um_wait(&w_empty[slot], (round - 1) & 1);
+                    if (um_elect()) {
+                        const uint32_t bytes = (uint32_t)(min(SPCW, jb.steps - s0) * N * 64);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(um_smem_u32(&w_full[slot])), "r"(bytes)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                                         sm_a + L::wring + slot * UM_WSLOT_BYTES),
+                                     "l"(a.w.wstream + jb.off + s0 * N * 64), "r"(bytes), "r"(um_smem_u32(&w_full[slot]))
+                                     : "memory");
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
+        }
+    } else if (warp == 2) {
+        // =========================== x0 tiles: one bulk copy per row (rows are padded in shared memory), one tile ahead ===========================
+        const float* src = a.x0 + (size_t)b * a.n_out * C;
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            const int t0 = t_first + tile * UM_TT;
+            if (tile >= 1) um_wait(&x_empty, (tile - 1) & 1);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(um_smem_u32(&x_full)), "r"((uint32_t)(UM_TT * C * 4))
+                             : "memory");
+            __syncwarp();
+            for (int r = lane; r < UM_TT; r += 32)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                                 sm_a + L::x0 + r * PX * 4),
+                             "l"(src + (size_t)(t0 + r) * C), "r"((uint32_t)(C * 4)), "r"(um_smem_u32(&x_full))
+                             : "memory");
         }
     } else if (warp == 0) {
         // =========================== MMA issue ===========================
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
+        constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(UM_ROWS >> 4) << 24);
         constexpr int SPC = UM_WSLOT_BYTES / (N * 64);       // k16 steps per weight chunk
         uint32_t wit = 0;
         uint32_t jobs_done[3] = {0, 0, 0};                    // per chain: selects the parity of a_ready
@@ -796,7 +896,8 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
 #pragma unroll 1
             for (int ji = 0; ji < 18; ++ji) {
                 const UmmaJob jb = a.w.jobs[ji];
-                const int c = jb.chain;
+                if (jb.chain < kc0 || jb.chain >= kc0 + NCH) continue;
+                const int c = jb.chain - kc0;
                 um_wait(&a_ready[c], jobs_done[c] & 1);
                 ++jobs_done[c];
                 if (lane == 0) UM_TRACE(ji * 4 + 0);
@@ -806,7 +907,7 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
                 const int lead = jb.conv2 ? (K - 1) : (K - 1) * 5;
                 const uint32_t abase = sm_a + (jb.conv2 ? (c == 0 ? L::a2(0) : c == 1 ? L::a2(1) : L::a2(2))
                                                         : (c == 0 ? L::a1(0) : c == 1 ? L::a1(1) : L::a1(2)));
-                const uint32_t d_tmem = tmem + (uint32_t)(c * 2 * N + (jb.conv2 ? 0 : N));     // row tile mt: + mt * 6 N columns
+                const uint32_t d_tmem = tmem + (uint32_t)(c * 4 * N + (jb.conv2 ? 0 : 2 * N));     // row tile mt: + mt * tile_cols
                 // Descriptors advance by plain additions on their 16-byte-unit address field:
                 //   C >= 16: step (tap, channel pair gq): +d rows per tap, +2 R rows per channel pair (two 8-channel groups)
                 //   C == 8 : step s covers taps 2s, 2s+1: +2 d rows per step, LBO = d rows
@@ -823,18 +924,17 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const int s1 = min(jb.steps, s0 + SPC);
                     if (um_elect()) {
-                        uint64_t dwh = um_desc(sm_a + L::wring + slot * UM_WSLOT_BYTES, N * 16);
+                        // weight step: [k group][hi rows 0..N-1 | lo rows N..2N-1][8]: one descriptor serves the stacked and the hi-only MMA
+                        uint64_t dwh = um_desc(sm_a + L::wring + slot * UM_WSLOT_BYTES, N * 32);
 #pragma unroll 2
                         for (int s = s0; s < s1; ++s) {
                             const uint64_t dah0 = dA0 + (uint64_t)(tap_off16 + gq * (uint32_t)(2 * R));
-                            const uint64_t dwl = dwh + (uint64_t)(N * 2);
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt) {       // the weight step is fetched once per 128-row tile
                                 const uint64_t dah = dah0 + (uint64_t)(mt * UM_ROWS), dal = dah + a_lo16;
-                                const uint32_t dt = d_tmem + (uint32_t)(mt * 6 * N);
-                                um_mma(dt, dal, dwh, idesc, first);
-                                um_mma(dt, dah, dwl, idesc, 1u);
-                                um_mma(dt, dah, dwh, idesc, 1u);
+                                const uint32_t dt = d_tmem + (uint32_t)(mt * L::tile_cols);
+                                um_mma(dt, dah, dwh, idesc2, first);
+                                um_mma(dt, dal, dwh, idesc, 1u);
                             }
                             first = 1u;
                             dwh += (uint64_t)(N * 4);
@@ -843,15 +943,8 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
                         um_commit(&w_empty[slot]);
                         if (s1 == jb.steps) um_commit(&d_ready[c]);
                     }
-                    // the other lanes advance the same counters
-                    const uint32_t adv = (uint32_t)(s1 - s0);
-                    {
-                        uint32_t t_adv = (gq + adv) / SPT;   // only the elected lane modified gq / tap_off16 above: recompute for all
-                        (void)t_adv;
-                    }
                     __syncwarp();
-                    // broadcast the elected lane's running state (it is the only one that advanced it)
-                    {
+                    {   // every lane tracks the position the elected lane has advanced to
                         const uint32_t steps_done = (uint32_t)s1;
                         gq = steps_done % SPT;
                         tap_off16 = (steps_done / SPT) * step_tap16;
@@ -862,36 +955,39 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
             }
         }
     } else if (warp >= 4) {
-        // =========================== epilogue (thread = time row x 8-channel group) ===========================
-        // G groups of 4 warps; group g owns channels 8g .. 8g+7 of all 128 rows (a warp may only touch the TMEM lane
-        // quadrant warp % 4, so each group is one full set of quadrants)
-        constexpr int NE = 128 * G * MT;
-        const int et = tid - 128, wg = (warp - 4) >> 2, g = wg % G, mt = wg / G, quad = warp & 3;
+        // =========================== epilogue (thread = time row x CPT channels) ===========================
+        // GE MT groups of 4 warps; a group owns CPT channels (S8 operand groups of 8) of the 128 rows of one MMA tile (a
+        // warp may only touch the TMEM lane quadrant warp % 4, so each group is one full set of quadrants)
+        constexpr int NE = 128 * GE * MT;
+        const int et = tid - 128, wg = (warp - 4) >> 2, ge = wg % GE, mt = wg / GE, quad = warp & 3;
+        const int g0 = ge * S8;                        // first 8-channel operand group of this thread
         const int pl = quad * 32 + lane;               // TMEM lane = row of the 128-row MMA tile
         const int p = mt * UM_ROWS + pl;               // row of the CTA tile
-        const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 6 * N);
-        uint32_t* xh = reinterpret_cast<uint32_t*>(sm + L::xin);
-        uint32_t* xl = xh + (NJ + 16) * PWI;
+        const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * L::tile_cols);
+        (void)pl;
         float* x0 = reinterpret_cast<float*>(sm + L::x0);
-        const size_t boff = (size_t)b * a.in_bstride;
-        float* dst = a.out + (size_t)b * a.n_out * C;
         uint32_t d_seen[3] = {0, 0, 0};
         auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(NE) : "memory"); };
 
-        // writes this thread's 8 channels of its row (already activated) into operand buffer `buf` (rows R, tile starts
+        // writes this thread's CPT channels of its row (already activated) into operand buffer `buf` (rows R, tile starts
         // at row `lead`), and the tail rows additionally into the saved context `ctx` (ctx_rows rows)
         auto write_rows = [&](int buf_off, int R, int lead, const float* y, int ctx_off, int ctx_rows) {
-            um_store8(sm + buf_off, G * R * 16, g * R + lead + p, y);
             const int cr = p - (UM_TT - ctx_rows);
-            if (cr >= 0) um_store8(sm + ctx_off, G * ctx_rows * 16, g * ctx_rows + cr, y);
+#pragma unroll
+            for (int s8 = 0; s8 < S8; ++s8) {
+                um_store8(sm + buf_off, G * R * 16, (g0 + s8) * R + lead + p, y + 8 * s8);
+                if (cr >= 0) um_store8(sm + ctx_off, G * ctx_rows * 16, (g0 + s8) * ctx_rows + cr, y + 8 * s8);
+            }
         };
         // copies the saved context (ctx_rows rows) in front of the tile rows of an operand buffer
         auto restore = [&](int buf_off, int R, int lead, int ctx_off, int ctx_rows) {
             if (p < ctx_rows) {
 #pragma unroll
                 for (int part = 0; part < 2; ++part)
-                    *reinterpret_cast<uint4*>(sm + buf_off + part * G * R * 16 + (g * R + lead - ctx_rows + p) * 16) =
-                        *reinterpret_cast<const uint4*>(sm + ctx_off + part * G * ctx_rows * 16 + (g * ctx_rows + p) * 16);
+#pragma unroll
+                    for (int s8 = 0; s8 < S8; ++s8)
+                        *reinterpret_cast<uint4*>(sm + buf_off + part * G * R * 16 + ((g0 + s8) * R + lead - ctx_rows + p) * 16) =
+                            *reinterpret_cast<const uint4*>(sm + ctx_off + part * G * ctx_rows * 16 + ((g0 + s8) * ctx_rows + p) * 16);
             }
         };
         auto publish = [&](int c) {   // operand buffer of chain c is complete: hand it to the MMA warp
@@ -900,106 +996,86 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
             __syncwarp();
             if (lane == 0) um_arrive(&a_ready[c]);
         };
-        auto load8 = [&](const float* ptr, float* o) {
-            const float4 u0 = __ldg(reinterpret_cast<const float4*>(ptr + 8 * g)), u1 = __ldg(reinterpret_cast<const float4*>(ptr + 8 * g) + 1);
-            o[0] = u0.x; o[1] = u0.y; o[2] = u0.z; o[3] = u0.w; o[4] = u1.x; o[5] = u1.y; o[6] = u1.z; o[7] = u1.w;
+        auto loadc = [&](const float* ptr, float* o) {      // this thread's CPT per-channel constants
+#pragma unroll
+            for (int q = 0; q < CPT / 4; ++q) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(ptr + CPT * ge) + q);
+                o[4 * q] = u.x; o[4 * q + 1] = u.y; o[4 * q + 2] = u.z; o[4 * q + 3] = u.w;
+            }
+        };
+        auto tld = [&](uint32_t taddr, float* o) {          // CPT accumulator columns: main + aux
+#pragma unroll
+            for (int s8 = 0; s8 < S8; ++s8) {
+                float aux[8];
+                um_ld8(taddr + 8 * s8, o + 8 * s8);
+                um_ld8(taddr + N + 8 * s8, aux);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[8 * s8 + i] += aux[i];
+            }
         };
         auto a1_off = [&](int c) { return c == 0 ? L::a1(0) : c == 1 ? L::a1(1) : L::a1(2); };
         auto a2_off = [&](int c) { return c == 0 ? L::a2(0) : c == 1 ? L::a2(1) : L::a2(2); };
         // context of the dilated conv of layer l: rows (K-1) d_l, stored after those of the earlier layers
-        auto c1_off = [&](int c, int l) {
-            const int K = um_K(c), rows_before = (K - 1) * (l == 0 ? 0 : l == 1 ? 1 : 4);
+        auto c1_off = [&](int c, int K, int l) {
+            const int rows_before = (K - 1) * (l == 0 ? 0 : l == 1 ? 1 : 4);
             return (c == 0 ? L::c1(0) : c == 1 ? L::c1(1) : L::c1(2)) + 2 * G * rows_before * 16;
         };
-        auto c2_off = [&](int c, int l) {
-            const int K = um_K(c);
-            return (c == 0 ? L::c2(0) : c == 1 ? L::c2(1) : L::c2(2)) + 2 * G * (K - 1) * l * 16;
-        };
+        auto c2_off = [&](int c, int K, int l) { return (c == 0 ? L::c2(0) : c == 1 ? L::c2(1) : L::c2(2)) + 2 * G * (K - 1) * l * 16; };
 
         for (int tile = 0; tile < n_tiles; ++tile) {
             const int t0 = t_first + tile * UM_TT;
             if (et == 0) UM_TRACE(72);
-            // ---- stage input rows j0-1 .. j0+TT/U-1: mean of the producer's partials, split to bf16 hi/lo ----
-            {
-                const int j_base = t0 / U - 1;
-                constexpr int V = CIN / 4;
-                for (int i = et; i < NJ * V; i += NE) {
-                    const int jj = i / V, c4 = i - jj * V;
-                    const int j = j_base + jj;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j >= 0 && j < a.n_in) {
-                        const size_t o = boff + (size_t)j * CIN + c4 * 4;
-                        v = __ldg(reinterpret_cast<const float4*>(a.in_p[0] + o));
-                        if (a.n_parts == 3) {
-                            const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.in_p[1] + o));
-                            const float4 v2 = __ldg(reinterpret_cast<const float4*>(a.in_p[2] + o));
-                            v.x = ((v.x + v1.x) + v2.x) / 3.0f; v.y = ((v.y + v1.y) + v2.y) / 3.0f;
-                            v.z = ((v.z + v1.z) + v2.z) / 3.0f; v.w = ((v.w + v1.w) + v2.w) / 3.0f;
-                        }
-                    }
-                    uint32_t h0, l0, h1, l1;
-                    split_pair(v.x, v.y, h0, l0);
-                    split_pair(v.z, v.w, h1, l1);
-                    *reinterpret_cast<uint2*>(xh + jj * PWI + c4 * 2) = make_uint2(h0, h1);
-                    *reinterpret_cast<uint2*>(xl + jj * PWI + c4 * 2) = make_uint2(l0, l1);
-                }
-            }
-            epi_bar();
-            // ---- ConvTranspose1d as U phase convolutions (mma.sync, all epilogue warps) -> x0[128][C] ----
-            {
-                constexpr int KC_UP = (2 * CIN) / 16, NT = C / 8;
-                const int rows = UM_TT / U, tiles = (rows + 15) / 16;
-                float2 bup[NT];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) bup[nt] = __ldg(reinterpret_cast<const float2*>(a.b_up + nt * 8 + 2 * (tid & 3)));
-                const uint32_t xh_a = um_smem_u32(xh), xl_a = um_smem_u32(xl);
-                for (int item = warp - 4; item < U * tiles; item += 4 * G * MT) {
-                    const int r = item / tiles, tl = item - r * tiles;
-                    const uint2* wh = a.upf_h + (size_t)r * KC_UP * NT * 32;
-                    const uint2* wl = a.upf_l + (size_t)r * KC_UP * NT * 32;
-                    mma_rows<CIN, C, 2, 1>(xh_a, xl_a, 1, wh, wl, 1, tl * 16, [&](int row, int nt, int co, float v0, float v1) {
-                        if (row < rows) *reinterpret_cast<float2*>(x0 + (U * row + r) * PX + co) = make_float2(v0 + bup[nt].x, v1 + bup[nt].y);
-                    });
-                }
-            }
             // contexts of the first dilated convs (layer 0) in front of the tiles
 #pragma unroll
-            for (int c = 0; c < 3; ++c) restore(a1_off(c), um_R1(c, UM_TT), (um_K(c) - 1) * 5, c1_off(c, 0), (um_K(c) - 1) * 1);
-            epi_bar();
-            // ---- x of the three resblocks = x0 (TMEM) and their first conv inputs ----
-            float xr[8];
-            {
-                const float4 u0 = *reinterpret_cast<const float4*>(x0 + p * PX + 8 * g), u1 = *reinterpret_cast<const float4*>(x0 + p * PX + 8 * g + 4);
-                xr[0] = u0.x; xr[1] = u0.y; xr[2] = u0.z; xr[3] = u0.w; xr[4] = u1.x; xr[5] = u1.y; xr[6] = u1.z; xr[7] = u1.w;
+            for (int c = 0; c < NCH; ++c) {
+                const int K = um_K(kc0 + c);
+                restore(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, c1_off(c, K, 0), (K - 1) * 1);
             }
+            um_wait(&x_full, tile & 1);
+            // ---- x of the resblocks = x0 (TMEM) and their first conv inputs ----
+            float xr[CPT];
+            const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                um_st8(t_lane + c * 2 * N + 8 * g, xr);
-                float ea[8], ieb[8], y[8];
-                load8(a.ea[c][0], ea);
-                load8(a.ieb[c][0], ieb);
+            for (int q = 0; q < CPT / 4; ++q) {
+                const float4 u = *reinterpret_cast<const float4*>(x0 + p * PX + CPT * ge + 4 * q);
+                xr[4 * q] = u.x; xr[4 * q + 1] = u.y; xr[4 * q + 2] = u.z; xr[4 * q + 3] = u.w;
+            }
+            epi_bar();                                  // all context rows restored before this tile's tails replace them
+            if (lane == 0) um_arrive(&x_empty);         // the loader may fetch the next tile
 #pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = snake_fast(xr[i], ea[i], ieb[i]);
-                write_rows(a1_off(c), um_R1(c, UM_TT), (um_K(c) - 1) * 5, y, c1_off(c, 0), (um_K(c) - 1) * 1);
+            for (int c = 0; c < NCH; ++c) {
+                const int kc = kc0 + c, K = um_K(kc);
+#pragma unroll
+                for (int s8 = 0; s8 < S8; ++s8) {
+                    um_st8(t_lane + c * 4 * N + CPT * ge + 8 * s8, xr + 8 * s8);
+                    um_st8(t_lane + c * 4 * N + N + CPT * ge + 8 * s8, zero8);      // the second convs accumulate onto [x | 0]
+                }
+                float ea[CPT], ieb[CPT], y[CPT];
+                loadc(a.ea[kc][0], ea);
+                loadc(a.ieb[kc][0], ieb);
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) y[i] = snake_fast(xr[i], ea[i], ieb[i]);
+                write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, y, c1_off(c, K, 0), (K - 1) * 1);
                 asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
                 publish(c);
             }
 
             if (et == 0) UM_TRACE(73);
-            float osum[8];
+            float osum[CPT];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) osum[i] = 0.f;
+            for (int i = 0; i < CPT; ++i) osum[i] = 0.f;
 #pragma unroll 1
             for (int ji = 0; ji < 18; ++ji) {
                 const UmmaJob jb = a.w.jobs[ji];
-                const int c = jb.chain, l = jb.layer, K = jb.K;
-                float v[8], pa[8], ea[8], ieb[8];
+                if (jb.chain < kc0 || jb.chain >= kc0 + NCH) continue;
+                const int kc = jb.chain, c = kc - kc0, l = jb.layer, K = jb.K;
+                float v[CPT], pa[CPT], ea[CPT], ieb[CPT];
                 // per-channel constants of this job are fetched while the MMAs are still running
                 if (!jb.conv2) {
-                    load8(a.w.b1[c][l], pa); load8(a.ea[c][2 * l + 1], ea); load8(a.ieb[c][2 * l + 1], ieb);
+                    loadc(a.w.b1[kc][l], pa); loadc(a.ea[kc][2 * l + 1], ea); loadc(a.ieb[kc][2 * l + 1], ieb);
                 } else {
-                    load8(a.w.bsum[c][l], pa);
-                    if (l < 2) { load8(a.ea[c][2 * (l + 1)], ea); load8(a.ieb[c][2 * (l + 1)], ieb); }
+                    loadc(a.w.bsum[kc][l], pa);
+                    if (l < 2) { loadc(a.ea[kc][2 * (l + 1)], ea); loadc(a.ieb[kc][2 * (l + 1)], ieb); }
                 }
                 um_wait(&d_ready[c], d_seen[c] & 1);
                 ++d_seen[c];
@@ -1007,38 +1083,42 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 if (!jb.conv2) {
                     // dilated conv done: + bias -> SnakeBeta -> input of the second conv
-                    restore(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, c2_off(c, l), K - 1);
-                    um_ld8(t_lane + c * 2 * N + N + 8 * g, v);
+                    restore(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, c2_off(c, K, l), K - 1);
+                    tld(t_lane + c * 4 * N + 2 * N + CPT * ge, v);
                     epi_bar();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
-                    write_rows(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, v, c2_off(c, l), K - 1);
+                    for (int i = 0; i < CPT; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
+                    write_rows(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, v, c2_off(c, K, l), K - 1);
                     publish(c);
                 } else {
                     // residual stream updated in TMEM: x_true = x + (sum of the second convs' biases so far)
                     const int ctx = (K - 1) * (l == 0 ? 3 : 5);
-                    if (l < 2) restore(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, c1_off(c, l + 1), ctx);
-                    um_ld8(t_lane + c * 2 * N + 8 * g, v);
+                    if (l < 2) restore(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, c1_off(c, K, l + 1), ctx);
+                    tld(t_lane + c * 4 * N + CPT * ge, v);
                     epi_bar();
                     if (l < 2) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
-                        write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, v, c1_off(c, l + 1), ctx);
+                        for (int i = 0; i < CPT; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
+                        write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, v, c1_off(c, K, l + 1), ctx);
                         publish(c);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) osum[i] += v[i] + pa[i];
+                        for (int i = 0; i < CPT; ++i) osum[i] += v[i] + pa[i];
                         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                     }
                 }
                 if (et == 0) UM_TRACE(ji * 4 + 3);
             }
-            // ---- mean of the three resblocks, channel-last (warm-up tiles are not written) ----
+            // ---- channel-last output (warm-up tiles are not written): the mean of the three resblocks, or this one's partial ----
             const int tg = t0 + p;
             if (t0 >= t_begin && tg < t_end) {
-                float4* o = reinterpret_cast<float4*>(dst + (size_t)tg * C + 8 * g);
-                o[0] = make_float4(osum[0] / 3.0f, osum[1] / 3.0f, osum[2] / 3.0f, osum[3] / 3.0f);
-                o[1] = make_float4(osum[4] / 3.0f, osum[5] / 3.0f, osum[6] / 3.0f, osum[7] / 3.0f);
+                const float sc = NCH == 3 ? 1.0f / 3.0f : 1.0f;
+                float* dst = a.out[NCH == 3 ? 0 : kc0] + (size_t)b * a.n_out * C + (size_t)tg * C + CPT * ge;
+#pragma unroll
+                for (int q = 0; q < CPT / 4; ++q)
+                    reinterpret_cast<float4*>(dst)[q] = NCH == 3 ? make_float4(osum[4 * q] / 3.0f, osum[4 * q + 1] / 3.0f, osum[4 * q + 2] / 3.0f, osum[4 * q + 3] / 3.0f)
+                                                                 : make_float4(osum[4 * q], osum[4 * q + 1], osum[4 * q + 2], osum[4 * q + 3]);
+                (void)sc;
             }
         }
     }
@@ -1049,26 +1129,27 @@ __global__ void __launch_bounds__(128 + 128 * (C / 8) * MT, 1) stage_umma_kernel
     }
 }
 
-template <int C, int U, int MT>
+template <int C, int U, int MT, int NCH>
 int launch_stage_umma(const UmmaStageArgs& a, int B, cudaStream_t stream) {
-    using L = UmLayout<C, U, MT>;
+    using L = UmLayout<C, U, MT, NCH>;
     constexpr int UM_TT = L::TT;
     static int sms = 0;
     if (!sms) {
-        BVC_CUDA(cudaFuncSetAttribute(stage_umma_kernel<C, U, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
+        BVC_CUDA(cudaFuncSetAttribute(stage_umma_kernel<C, U, MT, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
         int dev = 0;
         BVC_CUDA(cudaGetDevice(&dev));
         BVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     // time ranges per utterance: ~4 waves of CTAs, but ranges long enough that their warm-up (120 samples) stays small
+    const int ctas_per_range = 3 / NCH;
     const int tiles_total = (a.n_out + UM_TT - 1) / UM_TT;
-    const int want = (4 * sms + B - 1) / B;
+    const int want = (4 * sms + B * ctas_per_range - 1) / (B * ctas_per_range);
     const int max_ranges = tiles_total / 4 > 0 ? tiles_total / 4 : 1;
     int ranges = want < max_ranges ? want : max_ranges;
     if (ranges < 1) ranges = 1;
     const int tiles_per = (tiles_total + ranges - 1) / ranges;
     ranges = (tiles_total + tiles_per - 1) / tiles_per;
-    stage_umma_kernel<C, U, MT><<<dim3(ranges, B), 128 + 128 * L::G * MT, L::total, stream>>>(a);
+    stage_umma_kernel<C, U, MT, NCH><<<dim3(ranges, B, ctas_per_range), L::threads, L::total, stream>>>(a);
     BVC_CHECK_LAUNCH();
     return BVC_OK;
 }
@@ -1195,8 +1276,12 @@ size_t vocoder_workspace_floats(const VocoderWeights& w, int B, int T) {
     int C[5];
     vocoder_dims(w, T, n, C);
     size_t total = (size_t)B * (T + 6) * (w.n_mels + w.c0) + 256;
-    for (int i = 0; i < w.n_stages; ++i) total += 3 * ((size_t)B * C[i + 1] * n[i + 1] + 64);
-    return total;
+    size_t x0 = 0;
+    for (int i = 0; i < w.n_stages; ++i) {
+        total += 3 * ((size_t)B * C[i + 1] * n[i + 1] + 64);
+        x0 = std::max(x0, (size_t)B * C[i + 1] * n[i + 1] + (size_t)512 * C[i + 1] + 64);
+    }
+    return total + x0;
 }
 
 int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, const float* mel, int B, int T,
@@ -1213,6 +1298,11 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
     vb.pre = ws.take((size_t)B * (T + 6) * w.c0);
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 3; ++j) vb.part[i][j] = ws.take((size_t)B * vb.C[i + 1] * vb.n[i + 1]);
+    {   // upsampled stage input of the tcgen05 stage kernels (+ one tile of slack: whole tiles are copied)
+        size_t x0 = 0;
+        for (int i = 0; i < 4; ++i) x0 = std::max(x0, (size_t)B * vb.C[i + 1] * vb.n[i + 1] + (size_t)512 * vb.C[i + 1]);
+        vb.x0 = ws.take(x0);
+    }
 
     {
         const size_t total = (size_t)B * (T + 6) * X;
@@ -1231,25 +1321,44 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
     // Stages that run on the tcgen05 kernel (bit i = stage i).  Its MMAs fetch the 128 x 16 activation operand from
     // shared memory for every instruction (~64 clk measured), so with N = C_out it sustains ~40 C_out MAC/clk: twice the
     // mma.sync kernel at C = 32, on par at 16, behind at 8 where the per-job epilogue latency dominates.  Default: stage 1.
-    static const int umma_mask = getenv("BVC_VOC_UMMA") ? atoi(getenv("BVC_VOC_UMMA")) : 0x6;
+    static const int umma_mask = getenv("BVC_VOC_UMMA") ? atoi(getenv("BVC_VOC_UMMA")) : 0x7;
     bool single[4] = {false, false, false, false};     // stage i wrote one tensor (the mean) instead of three partials
     for (int i = 0; i < 4; ++i) {
-        if (precision >= 1 && ((umma_mask >> i) & 1) && i >= 1 && w.umma[i].ready) {
-            // all three resblocks of the stage in one tcgen05 kernel; the output is their mean
+        if (precision >= 1 && ((umma_mask >> i) & 1) && w.umma[i].ready) {
+            // tcgen05 stage kernel: C <= 32: all three resblocks per CTA, the output is their mean; C = 64: one resblock per CTA
+            const bool all_chains = vb.C[i + 1] <= 32;
+            UpsampleArgs up;
+            if (i == 0) {
+                up.n_parts = 1;
+                up.in_p[0] = up.in_p[1] = up.in_p[2] = vb.pre;
+                up.in_bstride = (long long)(T + 6) * w.c0;
+            } else {
+                up.n_parts = single[i - 1] ? 1 : 3;
+                for (int q = 0; q < 3; ++q) up.in_p[q] = vb.part[i - 1][single[i - 1] ? 0 : q];
+                up.in_bstride = (long long)vb.n[i] * vb.C[i];
+            }
+            up.n_in = (int)vb.n[i];
+            up.n_out = (int)vb.n[i + 1];
+            up.b_up = w.b_up[i];
+            up.upf_h = w.upf_h[i];
+            up.upf_l = w.upf_l[i];
+            up.x0 = vb.x0;
+            int rc;
+            switch (vb.C[i + 1]) {
+                case 64: rc = launch_upsample<64, 8>(up, B, stream); break;
+                case 32: rc = launch_upsample<32, 8>(up, B, stream); break;
+                case 16: rc = launch_upsample<16, 2>(up, B, stream); break;
+                default: rc = launch_upsample<8, 2>(up, B, stream); break;
+            }
+            if (rc != BVC_OK) return rc;
             UmmaStageArgs ua;
-            ua.n_parts = single[i - 1] ? 1 : 3;
-            for (int q = 0; q < 3; ++q) ua.in_p[q] = vb.part[i - 1][single[i - 1] ? 0 : q];
-            ua.in_bstride = (long long)vb.n[i] * vb.C[i];
-            ua.n_in = (int)vb.n[i];
+            ua.x0 = vb.x0;
             ua.n_out = (int)vb.n[i + 1];
-            ua.b_up = w.b_up[i];
-            ua.upf_h = w.upf_h[i];
-            ua.upf_l = w.upf_l[i];
             for (int cc = 0; cc < 3; ++cc) {
                 const AmpBlockWeights& bw = w.blocks[i * 3 + (2 - cc)];
                 for (int q = 0; q < 6; ++q) { ua.ea[cc][q] = bw.act[q].ea; ua.ieb[cc][q] = bw.act[q].inv_eb; }
+                ua.out[cc] = all_chains ? vb.part[i][0] : vb.part[i][2 - cc];     // chain cc = resblock kernel index 2 - cc
             }
-            ua.out = vb.part[i][0];
             ua.w = w.umma[i];
             ua.trace = nullptr;
             static unsigned long long* trace_dev = nullptr;
@@ -1259,11 +1368,11 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
                 BVC_CUDA(cudaMemsetAsync(trace_dev, 0, 80 * sizeof(unsigned long long), stream));
                 ua.trace = trace_dev;
             }
-            int rc;
             switch (vb.C[i + 1]) {
-                case 32: rc = launch_stage_umma<32, 8, 1>(ua, B, stream); break;
-                case 16: rc = launch_stage_umma<16, 2, 2>(ua, B, stream); break;
-                default: rc = launch_stage_umma<8, 2, 4>(ua, B, stream); break;
+                case 64: rc = launch_stage_umma<64, 8, 1, 1>(ua, B, stream); break;
+                case 32: rc = launch_stage_umma<32, 8, 1, 3>(ua, B, stream); break;
+                case 16: rc = launch_stage_umma<16, 2, 2, 3>(ua, B, stream); break;
+                default: rc = launch_stage_umma<8, 2, 2, 3>(ua, B, stream); break;
             }
             if (rc != BVC_OK) return rc;
             if (tracing) {   // per job: MMA warp got the operand / issued all MMAs, epilogue saw the result / finished
@@ -1273,12 +1382,15 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
                 const unsigned long long z = hbuf[72];
                 fprintf(stderr, "stage %d tile trace (us): prologue %.2f\n", i, (hbuf[73] - z) / 1e3);
                 for (int ji = 0; ji < 18; ++ji)
-                    fprintf(stderr, "  job %2d chain %d layer %d conv%d steps %2d: mma_start %6.2f mma_issued %6.2f epi_start %6.2f epi_done %6.2f\n", ji,
-                            ua.w.jobs[ji].chain, ua.w.jobs[ji].layer, ua.w.jobs[ji].conv2 + 1, ua.w.jobs[ji].steps, (hbuf[ji * 4] - z) / 1e3,
-                            (hbuf[ji * 4 + 1] - z) / 1e3, (hbuf[ji * 4 + 2] - z) / 1e3, (hbuf[ji * 4 + 3] - z) / 1e3);
+                    if (hbuf[ji * 4])
+                        fprintf(stderr, "  job %2d chain %d layer %d conv%d steps %2d: mma_start %6.2f mma_issued %6.2f epi_start %6.2f epi_done %6.2f\n", ji,
+                                ua.w.jobs[ji].chain, ua.w.jobs[ji].layer, ua.w.jobs[ji].conv2 + 1, ua.w.jobs[ji].steps, (hbuf[ji * 4] - z) / 1e3,
+                                (hbuf[ji * 4 + 1] - z) / 1e3, (hbuf[ji * 4 + 2] - z) / 1e3, (hbuf[ji * 4 + 3] - z) / 1e3);
             }
-            vb.part[i][1] = vb.part[i][2] = vb.part[i][0];   // parity taps read "three partials": all the same mean
-            single[i] = true;
+            if (all_chains) {
+                vb.part[i][1] = vb.part[i][2] = vb.part[i][0];   // parity taps read "three partials": all the same mean
+                single[i] = true;
+            }
             continue;
         }
         for (int jj = 0; jj < 3; ++jj) {
