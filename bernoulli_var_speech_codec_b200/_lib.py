@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libbvc.so")
+LIB_PATH = os.environ.get("BVC_LIBRARY") or os.path.join(PKG, "libbvc.so")   # BVC_LIBRARY: another build of the same ABI (A/B timing)
 
 BVC_OK = 0
 STATUS_NAMES = {0: "BVC_OK", -1: "BVC_ERR_INVALID", -2: "BVC_ERR_SCHEMA", -3: "BVC_ERR_DEVICE",
@@ -42,6 +42,7 @@ SYMBOLS = {
     "bvc_set_frontend": (C.c_int, [_P, _P, _P]),
     "bvc_logmel": (C.c_int, [_P, _P, _I, _I, _F, _P, _P]),
     "bvc_encode": (C.c_int, [_P, _P, _P, _F, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "bvc_encode_mel": (C.c_int, [_P, _P, _P, _F, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "bvc_unpack_codes": (C.c_int, [_P, _P, _P, _F, _I, _I, _P, _P]),
     "bvc_decode_mel": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "bvc_vocode": (C.c_int, [_P, _P, _I, _I, _I, _F, _P, _P]),

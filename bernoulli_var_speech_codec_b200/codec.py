@@ -191,7 +191,9 @@ class _Engine:
                        "mel_spectrogram")
         return mel
 
-    def encode(self, mel, bits, bits_scalar, h0, want_logits=False, want_all_h=True, want_packed=False):
+    def encode(self, mel, bits, bits_scalar, h0, want_logits=False, want_all_h=True, want_packed=False, want_mel=False):
+        """-> (codes, all_h, h_final, logits, packed[, mel_hat]); mel_hat (want_mel) is the decoder's mel the encoder forms
+        inside its loop (bvrnn.py:198-206) = BVRNN.decode(codes, h0)[0]."""
         mel = self._dev(mel, "y")
         B, T, _ = mel.shape
         dev = self.device
@@ -202,10 +204,13 @@ class _Engine:
         h_fin = torch.empty(B, self.H, device=dev, dtype=torch.float32)
         bits_t = self._dev(bits, "varBitrate") if bits is not None else None
         h0_t = self._dev(h0, "h") if h0 is not None else None
+        mel_hat = torch.empty(B, T, self.X, device=dev, dtype=torch.float32) if want_mel else None
         with torch.cuda.device(dev):
-            _lib.check(self.lib.bvc_encode(self.handle, _ptr(mel), _ptr(bits_t), float(bits_scalar), _ptr(h0_t), B, T,
-                                           _ptr(codes), _ptr(packed), _ptr(logits), _ptr(all_h), _ptr(h_fin),
-                                           _stream(dev)), "BVRNN.encode")
+            _lib.check(self.lib.bvc_encode_mel(self.handle, _ptr(mel), _ptr(bits_t), float(bits_scalar), _ptr(h0_t), B, T,
+                                               _ptr(codes), _ptr(packed), _ptr(logits), _ptr(all_h), _ptr(h_fin),
+                                               _ptr(mel_hat), _stream(dev)), "BVRNN.encode")
+        if want_mel:
+            return codes, all_h, h_fin, logits, packed, mel_hat
         return codes, all_h, h_fin, logits, packed
 
     def unpack_codes(self, packed, bits, bits_scalar):
@@ -365,9 +370,16 @@ class BVRNNCodecModel(nn.Module):
         return self._engine.vocode(mel, length, SCALING)
 
     def forward(self, x, bitrate):
+        """decode(encode(x, bitrate), x.shape[1]) (reference :73-76) with ONE recurrence: the encoder already forms the
+        decoder's mel for these codes inside its loop (analysis by synthesis, bvrnn.py:198-206 vs 222-227), so
+        the vocoder is fed from the encode kernel's side output instead of running BVRNN.decode again.  Calling encode()
+        and decode() separately runs both recurrences, as it must."""
         length = x.shape[1]
-        codes = self.encode(x, bitrate)
-        return self.decode(codes, length)
+        on_cpu = x.device.type == "cpu"
+        mel = self._engine.logmel(x.to(self.device), SCALING)
+        out = self._engine.encode(mel, None, self.bits_per_frame(bitrate), None, want_all_h=False, want_mel=True)
+        wav = self._engine.vocode(out[5], length, SCALING)
+        return wav.cpu() if on_cpu else wav
 
     # ---- packed wire format (SURVEY.md 8f; not in the reference, which moves 256 B of floats per 35-bit frame) ----
     def encode_packed(self, x, bitrate):

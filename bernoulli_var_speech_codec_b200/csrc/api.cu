@@ -764,6 +764,13 @@ int bvc_logmel(bvc_handle* h, const float* x_dev, int32_t B, int32_t L, float sc
 int bvc_encode(bvc_handle* h, const float* mel_dev, const float* bits_dev, float bits_scalar, const float* h0_dev,
                int32_t B, int32_t T, float* codes_dev, uint64_t* packed_dev, float* logits_dev, float* all_h_dev,
                float* h_final_dev, void* stream) {
+    return bvc_encode_mel(h, mel_dev, bits_dev, bits_scalar, h0_dev, B, T, codes_dev, packed_dev, logits_dev, all_h_dev,
+                          h_final_dev, nullptr, stream);
+}
+
+int bvc_encode_mel(bvc_handle* h, const float* mel_dev, const float* bits_dev, float bits_scalar, const float* h0_dev,
+                   int32_t B, int32_t T, float* codes_dev, uint64_t* packed_dev, float* logits_dev, float* all_h_dev,
+                   float* h_final_dev, float* mel_hat_dev, void* stream) {
     REQUIRE(h && mel_dev && codes_dev, BVC_ERR_INVALID, "bvc_encode: null argument");
     REQUIRE(h->have_bvrnn, BVC_ERR_STATE, "bvc_encode: BVRNN weights not loaded");
     REQUIRE(B > 0 && T >= 0, BVC_ERR_INVALID, "bvc_encode: bad B/T");
@@ -774,7 +781,7 @@ int bvc_encode(bvc_handle* h, const float* mel_dev, const float* bits_dev, float
     if (rc) return rc;
     if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
     rc = bvrnn_encode(h->bw, h->ws, mel_dev, bits_dev, bits_scalar, h0_dev, B, T, codes_dev,
-                      (unsigned long long*)packed_dev, logits_dev, all_h_dev, h_final_dev, h->precision,
+                      (unsigned long long*)packed_dev, logits_dev, all_h_dev, h_final_dev, mel_hat_dev, h->precision,
                       (cudaStream_t)stream);
     if (rc) return rc;
     return ws_release(h, (cudaStream_t)stream);
@@ -852,7 +859,7 @@ int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, fl
     if (rc) return rc;
     if (T > 0) {
         rc = bvrnn_encode(h->bw, h->ws, mel, nullptr, bits_scalar, nullptr, B, T, codes, nullptr, nullptr, nullptr,
-                          nullptr, h->precision, s);
+                          nullptr, nullptr, h->precision, s);
         if (rc) return rc;
         BVC_CUDA(cudaMemcpyAsync(codes_host, codes, ncodes * sizeof(float), cudaMemcpyDeviceToHost, s));
     }

@@ -445,7 +445,7 @@ static int persistent_max_rows(int n_clusters) {
 static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits,
                                    float bits_scalar, const float* h0, int B, int T, float* codes,
                                    unsigned long long* packed, float* logits, float* all_h, float* h_final,
-                                   cudaStream_t s) {
+                                   float* mel_hat, cudaStream_t s) {
     const int H = w.H, X = w.X, Z = w.Z;
     const size_t BT = (size_t)B * T;
     RecurrentWeights& rw = w.rw;
@@ -481,7 +481,7 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     rec::Frame& fr = p->frame;
     fr.M = B; fr.T = T; fr.X = X; fr.Z = Z; fr.H = H; fr.var_bit = w.var_bit;
     fr.bits_scalar = bits_scalar; fr.bits = bits; fr.codes = codes; fr.packed = packed; fr.logits = logits;
-    fr.all_h = all_h; fr.h = hf; fr.h_img = hI; fr.gh = gh; fr.mel_out = nullptr;
+    fr.all_h = all_h; fr.h = hf; fr.h_img = hI; fr.gh = gh; fr.mel_out = mel_hat;
 
     ProgramBuilder pb;
     pb.p = p; pb.n_clusters = G; pb.M = B;
@@ -514,6 +514,15 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     const int op_d3 = pb.add_op(linear_op(rw.d4, w.b_d4, 1, d3I, KH));
     // phi_x.0 of the reconstruction, fused with dec.6 and the mel normalisation (bvrnn.py:202-204)
     const int op_x1 = pb.add_op(linear_op(rw.x1f, rw.b_x1f, 1, x1I, KH));
+    // The encoder runs the decoder inside its loop (analysis by synthesis, bvrnn.py:198-206): dec_t is exactly the mel
+    // BVRNN.decode would compute from these codes and the same h0.  Encoding alone never forms it (x1f skips it); the
+    // fused forward asks for it as a side output, like the decode program does.
+    int op_mel = -1;
+    if (mel_hat) {
+        o = linear_op(rw.d6, rw.b_d6p, 0, nullptr, 0);
+        o.kind = rec::KIND_MEL;
+        op_mel = pb.add_op(o);
+    }
     const int op_x2 = pb.add_op(linear_op(rw.px2, w.b_px2, 1, x2I, KH));
     const int op_px = pb.add_op(linear_op(rw.px4, w.b_px4, 1, pxI, KH));
     o = linear_op(rw.ihx_q, nullptr, 0, hI, KH);
@@ -530,7 +539,8 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     pb.add_phase(pzI, H, 1, {op_d1, op_giz});
     pb.add_phase(d1I, H, 1, {op_d2});
     pb.add_phase(d2I, H, 1, {op_d3});
-    pb.add_phase(d3I, H, 1, {op_x1});
+    if (op_mel >= 0) pb.add_phase(d3I, H, 1, {op_x1, op_mel});
+    else pb.add_phase(d3I, H, 1, {op_x1});
     pb.add_phase(x1I, H, 1, {op_x2});
     pb.add_phase(x2I, H, 1, {op_px});
     pb.add_phase(pxI, H, 1, {op_gru});
@@ -608,10 +618,17 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
 
 int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
-                 float* all_h, float* h_final, int precision, cudaStream_t s) {
-    if (!(precision >= 1 && w.rw.ready))
-        return bvrnn_encode_layers(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final,
-                                   precision, s);
+                 float* all_h, float* h_final, float* mel_hat, int precision, cudaStream_t s) {
+    if (!(precision >= 1 && w.rw.ready)) {
+        const size_t mark = ws.used;
+        BVC_TRY(bvrnn_encode_layers(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final,
+                                    precision, s));
+        if (mel_hat) {      // the layer-by-layer path keeps the second recurrence (same result, bvrnn.py:198-206 vs 222-227)
+            ws.used = mark;
+            BVC_TRY(bvrnn_decode_layers(w, ws, codes, h0, B, T, mel_hat, nullptr, precision, s));
+        }
+        return BVC_OK;
+    }
     int G = 0;
     BVC_TRY(cluster_count(&G));
     const int max_rows = persistent_max_rows(G);
@@ -623,7 +640,8 @@ int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* 
         BVC_TRY(bvrnn_encode_persistent(w, ws, mel + r * T_ * w.X, bits ? bits + r * T_ : nullptr, bits_scalar,
                                         h0 ? h0 + r * w.H : nullptr, nb, T, codes + r * T_ * w.Z,
                                         packed ? packed + r * T_ : nullptr, logits ? logits + r * T_ * w.Z : nullptr,
-                                        all_h ? all_h + r * T_ * w.H : nullptr, h_final ? h_final + r * w.H : nullptr, s));
+                                        all_h ? all_h + r * T_ * w.H : nullptr, h_final ? h_final + r * w.H : nullptr,
+                                        mel_hat ? mel_hat + r * T_ * w.X : nullptr, s));
     }
     return BVC_OK;
 }

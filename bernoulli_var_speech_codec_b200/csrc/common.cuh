@@ -152,7 +152,7 @@ int unpack_codes(const unsigned long long* packed, const float* bits, float bits
                  int Z, float* codes, cudaStream_t s);
 int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
-                 float* all_h, float* h_final, int precision, cudaStream_t stream);
+                 float* all_h, float* h_final, float* mel_hat, int precision, cudaStream_t stream);
 int bvrnn_decode(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T,
                  float* mel, float* h_final, int precision, cudaStream_t stream);
 

@@ -65,6 +65,18 @@ struct Bars {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// non-blocking poll (a try_wait round trip is ~100 clk: polls of several barriers are issued back to back)
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -711,7 +723,8 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     } else if (warp == 0) {
         // =========================== MMA warp ===========================
         uint32_t wIt = 0, accIt = 0;
-        uint32_t aUse[A_SLOTS] = {0, 0, 0, 0};
+        uint32_t aPar = 0;       // bit c = parity of the next completion of fullA[c] (a register: an indexed array would live in local
+                                 // memory, and with ~28 KiB of L1 left next to 228 KiB of shared memory its loads come back from L2)
         bool dead = false;
         const uint64_t descA = make_desc(smem_base + SMEM_A), descW = make_desc(smem_base + SMEM_W);
         for (int t = 0; t < T && !dead; ++t) {
@@ -726,15 +739,26 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     tc_fence_after();
                     const uint32_t idesc = make_idesc(TILE_M, bn);
                     const uint32_t d_tmem = tmem + slot * ACC_COLS;
+                    // The tensor pipe runs dry whenever this warp is not issuing (an MMA issues in ~55 clk and executes in ~72), so
+                    // the chunks that have already landed are found with one batch of polls instead of one blocking wait each.
+                    uint32_t okW = 0, okA = j == 0 ? 0u : 0xFu;
+#pragma unroll
+                    for (int i = 0; i < A_SLOTS; ++i)
+                        if (i < nck) okW |= mbar_test(&bars.fullW[(wIt + i) % W_SLOTS], ((wIt + i) / W_SLOTS) & 1u) << i;
                     for (int c = 0; c < nck; ++c) {
                         if (j == 0) {
-                            if (!mbar_wait<false>(&bars.fullA[c], aUse[c] & 1, abort_flag, 22)) { dead = true; break; }
-                            ++aUse[c];
+                            if (!((okA >> c) & 1u) && !mbar_wait<false>(&bars.fullA[c], (aPar >> c) & 1u, abort_flag, 22)) { dead = true; break; }
+                            if (c == 0) {
+#pragma unroll
+                                for (int i = 1; i < A_SLOTS; ++i)
+                                    if (i < nck) okA |= mbar_test(&bars.fullA[i], (aPar >> i) & 1u) << i;
+                            }
+                            aPar ^= 1u << c;
                             if (lane == 0 && c == 0) BVC_TRACE(5);
                             if (lane == 0 && c == nck - 1) BVC_TRACE(6);
                         }
                         const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
-                        if (!mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
+                        if (!((okW >> c) & 1u) && !mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
                         ++wIt;
                         tc_fence_after();
                         if (elect_one()) {

@@ -117,6 +117,15 @@ int bvc_encode(bvc_handle* h, const float* mel_dev, const float* bits_dev, float
                float* codes_dev, uint64_t* packed_dev, float* logits_dev,
                float* all_h_dev, float* h_final_dev, void* stream);
 
+/* bvc_encode that also returns the decoder's mel (fused forward, new).  The reference's encoder runs the decoder inside
+ * its loop (analysis by synthesis, bvrnn.py:198-206): the dec_t it forms is exactly what BVRNN.decode (bvrnn.py:222-227)
+ * recomputes from the same codes and h0, so forward() = decode(encode(x)) (bvrnn_codec_model.py:73-76) needs only one
+ * recurrence.  mel_hat_dev [B,T,x_dim] or NULL (then identical to bvc_encode). */
+int bvc_encode_mel(bvc_handle* h, const float* mel_dev, const float* bits_dev, float bits_scalar,
+                   const float* h0_dev, int32_t B, int32_t T,
+                   float* codes_dev, uint64_t* packed_dev, float* logits_dev,
+                   float* all_h_dev, float* h_final_dev, float* mel_hat_dev, void* stream);
+
 /* Wire format (new; the reference only has the float layout): one uint64 per frame, bit i = code i, masked bits 0.
  * bvc_encode fills packed_dev; this expands it back to the reference's float codes ({0,1}, 0.5 for bits >= budget,
  * bvrnn.py:191-196) so that bvc_decode_mel can consume it.  bits_dev [B,T] or NULL -> bits_scalar. */

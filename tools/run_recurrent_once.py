@@ -23,10 +23,12 @@ for _ in range(a.reps):
     e0.record()
     codes = m._engine.encode(mel, None, 35.0, None, want_all_h=False)[0]
     e1.record()
+    enc_ms = m._engine.last_recurrent_ms()
     dmel, _ = m._engine.decode_mel(codes, None)
     e2.record()
+    dec_ms = m._engine.last_recurrent_ms()
 torch.cuda.synchronize()
 T = codes.shape[1]
 print("ok", tuple(codes.shape), "encode %.2f ms (%.1f us/frame)  decode_mel %.2f ms (%.1f us/frame)  flags=%s" % (
     e0.elapsed_time(e1), 1e3 * e0.elapsed_time(e1) / T, e1.elapsed_time(e2), 1e3 * e1.elapsed_time(e2) / T,
-    os.environ.get("BVC_REC_DEBUG", "0")))
+    os.environ.get("BVC_REC_DEBUG", "0")), " recurrent kernels: encode %.1f us/frame, decode %.1f us/frame" % (1e3 * enc_ms / T, 1e3 * dec_ms / T))
