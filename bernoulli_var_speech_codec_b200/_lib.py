@@ -23,6 +23,7 @@ class BvcConfig(C.Structure):
         ("voc_initial_channel", C.c_int32), ("voc_num_stages", C.c_int32),
         ("voc_up_rates", C.c_int32 * 4), ("voc_up_kernels", C.c_int32 * 4),
         ("voc_num_kernels", C.c_int32), ("voc_res_kernels", C.c_int32 * 3), ("voc_res_dilations", C.c_int32 * 3),
+        ("voc_antialias", C.c_int32 * 4), ("voc_antialias_post", C.c_int32),
     ]
 
 

@@ -94,15 +94,14 @@ class _Engine:
     def __init__(self, conf: dict, device: torch.device):
         self.lib = _lib.load()
         self.pinned = _PinnedPool(self.lib)
-        if self.lib.bvc_abi_version() != 1:
+        if self.lib.bvc_abi_version() != 2:
             raise RuntimeError("libbvc ABI version mismatch")
         v = conf["vocoder_config"]
         if v.get("activation", "snakebeta") != "snakebeta" or not v.get("snake_logscale", True):
             raise NotImplementedError("only the shipped log-scale snakebeta activation is implemented")
-        for key in ("layers_sym", "layers_antialias"):
-            if any(v.get(key, [])):
-                raise NotImplementedError(f"vocoder_config.{key}=true is not implemented (shipped configs use false)")
-        for key in ("pre_sym", "post_sym", "antialias_post"):
+        if any(v.get("layers_sym", [])):
+            raise NotImplementedError("vocoder_config.layers_sym=true is not implemented (shipped configs use false)")
+        for key in ("pre_sym", "post_sym"):
             if v.get(key, False):
                 raise NotImplementedError(f"vocoder_config.{key}=true is not implemented (shipped configs use false)")
         if str(v.get("resblock", "1")) != "1":
@@ -126,6 +125,8 @@ class _Engine:
         cfg.voc_num_kernels = 3
         cfg.voc_res_kernels = (C.c_int32 * 3)(*v["resblock_kernel_sizes"])
         cfg.voc_res_dilations = (C.c_int32 * 3)(*dil[0])
+        cfg.voc_antialias = (C.c_int32 * 4)(*[int(bool(a)) for a in v.get("layers_antialias", [False] * 4)])
+        cfg.voc_antialias_post = int(bool(v.get("antialias_post", False)))
         self.handle = C.c_void_p()
         _lib.check(self.lib.bvc_create(C.byref(self.handle), C.byref(cfg)), "bvc_create")
         self.device = device

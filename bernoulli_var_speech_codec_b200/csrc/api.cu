@@ -537,6 +537,18 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
         ex.push_back({name + ".weight_v", {d0, d1, k}});
         ex.push_back({name + ".bias", {nb}});
     };
+    // SnakeBeta, or Activation1d wrapping it (models.py:66-88): `.act.alpha/.act.beta` + two registered filter buffers
+    std::string aa_first;
+    auto act_schema = [&](const std::string& name, int64_t C, bool aa) {
+        const std::string inner = aa ? name + ".act" : name;
+        ex.push_back({inner + ".alpha", {C}});
+        ex.push_back({inner + ".beta", {C}});
+        if (aa) {
+            ex.push_back({name + ".upsample.filter", {1, 1, 12}});
+            ex.push_back({name + ".downsample.lowpass.filter", {1, 1, 12}});
+            if (aa_first.empty()) aa_first = name;
+        }
+    };
     wn("conv_pre", C0, X, 7, C0);
     int64_t ch = C0;
     for (int i = 0; i < c.voc_num_stages; ++i) {
@@ -549,14 +561,10 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
                 wn(rb + ".convs1." + std::to_string(l), ch, ch, c.voc_res_kernels[j], ch);
                 wn(rb + ".convs2." + std::to_string(l), ch, ch, c.voc_res_kernels[j], ch);
             }
-            for (int a = 0; a < 6; ++a) {
-                ex.push_back({rb + ".activations." + std::to_string(a) + ".alpha", {ch}});
-                ex.push_back({rb + ".activations." + std::to_string(a) + ".beta", {ch}});
-            }
+            for (int a = 0; a < 6; ++a) act_schema(rb + ".activations." + std::to_string(a), ch, c.voc_antialias[i] != 0);
         }
     }
-    ex.push_back({"activation_post.alpha", {ch}});
-    ex.push_back({"activation_post.beta", {ch}});
+    act_schema("activation_post", ch, c.voc_antialias_post != 0);
     wn("conv_post", 1, ch, 7, 1);
     rc = check_schema(m, ex);
     if (rc) return rc;
@@ -640,7 +648,8 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
                 bw.w2[l] = pack(rb + ".convs2." + std::to_string(l), &bw.f2h[l], &bw.f2l[l]);
                 bw.b2[l] = up(to_vec(m[rb + ".convs2." + std::to_string(l) + ".bias"]));
             }
-            for (int a = 0; a < 6; ++a) snake(rb + ".activations." + std::to_string(a), ch, &bw.act[a]);
+            for (int a = 0; a < 6; ++a)
+                snake(rb + ".activations." + std::to_string(a) + (c.voc_antialias[i] ? ".act" : ""), ch, &bw.act[a]);
         }
     }
     // ---- tcgen05 stage kernel (vocoder.cu, stage_umma_kernel): weight stream in MMA issue order ----
@@ -700,7 +709,24 @@ int bvc_load_vocoder(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
         }
         um.ready = ok;
     }
-    snake("activation_post", ch, &w.act_post);
+    snake(c.voc_antialias_post ? "activation_post.act" : "activation_post", ch, &w.act_post);
+    for (int i = 0; i < 4; ++i) w.antialias[i] = i < c.voc_num_stages && c.voc_antialias[i] != 0;
+    w.antialias_post = c.voc_antialias_post != 0;
+    if (!aa_first.empty()) {
+        // every Activation1d of the reference is built with the same filter (act.py:10-21); the buffers of the first one
+        // are used for all, after checking that the others carry the same values
+        const HostTensor &fu = m[aa_first + ".upsample.filter"], &fd = m[aa_first + ".downsample.lowpass.filter"];
+        for (int q = 0; q < 12; ++q) { w.aa_up[q] = fu.data[q]; w.aa_down[q] = fd.data[q]; }
+        for (const auto& kv : m) {
+            const std::string& nm = kv.first;
+            const bool is_up = nm.size() > 16 && nm.compare(nm.size() - 16, 16, ".upsample.filter") == 0;
+            const bool is_dn = nm.size() > 26 && nm.compare(nm.size() - 26, 26, ".downsample.lowpass.filter") == 0;
+            if (!is_up && !is_dn) continue;
+            for (int q = 0; q < 12; ++q)
+                REQUIRE(kv.second.data[q] == (is_up ? w.aa_up[q] : w.aa_down[q]), BVC_ERR_SCHEMA,
+                        "anti-aliasing filters differ between activations; this build expects one shared filter");
+        }
+    }
     w.w_post = up(folded("conv_post"));   // [1, ci, 7] is already [ci][tap]
     w.b_post = up(to_vec(m["conv_post.bias"]));
     REQUIRE(ok, BVC_ERR_NOMEM, "device allocation failed while loading vocoder weights");

@@ -198,6 +198,9 @@ struct VocoderWeights {
     uint2 *upf_h[4], *upf_l[4];   // per output phase r: 2-tap fragment-packed weights (taps r+U, r), phases concatenated
     AmpBlockWeights blocks[12];
     UmmaStageWeights umma[4];
+    bool antialias[4] = {false, false, false, false};   // stage i: Activation1d around every SnakeBeta of its resblocks
+    bool antialias_post = false;                        // ... and around activation_post
+    float aa_up[12], aa_down[12];                       // the checkpoint's 12-tap Kaiser-sinc filters (up / down sampling)
     SnakeParams act_post;
     float* w_post = nullptr;  // [ci][tap]
     float* b_post = nullptr;  // [1]
@@ -205,6 +208,8 @@ struct VocoderWeights {
 struct VocoderBuffers {       // views into the workspace, valid after the last vocoder_forward
     float* mel_pad = nullptr; // [B, T+6, n_mels]
     float* pre = nullptr;     // [B, T+6, c0] channel-last (rows t >= T of each utterance are scratch)
+    float* aa_a = nullptr;    // [B, n, C] scratch of the layer-by-layer anti-aliased stages
+    float* aa_b = nullptr;
     float* x0 = nullptr;      // [B, n, C] output of a stage's transposed convolution (tcgen05 stage kernels; reused by every stage)
     float* part[4][3];        // per stage, per resblock: [B, n, C] channel-last
     int64_t n[5];             // n[0] = T, n[i+1] = length after stage i

@@ -28,6 +28,8 @@
 
 #include "common.cuh"
 
+#define BVC_TRY(x) do { int rc_try_ = (x); if (rc_try_ != BVC_OK) return rc_try_; } while (0)
+
 namespace bvc {
 
 namespace {
@@ -1154,11 +1156,227 @@ int launch_stage_umma(const UmmaStageArgs& a, int B, cudaStream_t stream) {
     return BVC_OK;
 }
 
+// ===========================================================================
+// Anti-aliased activation (reference alias_free_torch/act.py:8-28) and the layer-by-layer stages that use it
+// ===========================================================================
+// Activation1d = 2x FIR up-sampling -> SnakeBeta -> 2x FIR down-sampling, per channel, with replicate padding at the
+// utterance edges (resample.py:24-32, filter.py:88-96).  With the 12-tap filter f, for a sequence x[0..n):
+//   u[2t]   = 2 sum_q f[2q+1] x[t+2-q],   u[2t+1] = 2 sum_q f[2q] x[t+3-q]      (q = 0..5, x index clamped to [0, n))
+//   a[i]    = snakebeta(u[i])                                                    (i in [0, 2n))
+//   y[t]    = sum_k g[k] a[clamp(2t + k - 5, 0, 2n - 1)]                         (k = 0..11)
+// so y[t] looks 6 samples ahead: the activation is not causal, which is why these stages cannot use the time-streaming
+// kernels (they carry left contexts only) and run layer by layer through HBM instead.  One kernel does the whole
+// activation in shared memory: x tile (+-6 rows) -> u, a at the doubled rate -> y; HBM traffic = one read + one write.
+struct AaArgs {
+    const float* in_p[3];   // [B, n, C] channel-last; n_parts = 3: the mean of three tensors is activated
+    int n_parts;
+    int n;
+    const float* ea;        // exp(alpha), 1 / (exp(beta) + 1e-9) per channel
+    const float* ieb;
+    float fu[12], fd[12];
+    float* out;             // [B, n, C]
+};
+
+template <int C>
+struct AaLayout {
+    static constexpr int TT = 4096 / C;          // output rows per CTA
+    static constexpr int S1 = (TT + 6 + 3) / 4;  // strips of 4 low-rate positions t = t0 - 3 + 4 s + j: a[2t], a[2t+1] each
+    static constexpr int XR = 4 * S1 + 6;        // x rows t0 - 6 ..
+    static constexpr int AR = 8 * S1;            // a rows 2 t0 - 6 .. (row 0 is one more than the 2 t0 - 5 the filters reach)
+    static constexpr int P = C + 4;              // row pitch in floats: float4-aligned, consecutive strips hit different banks
+    static constexpr size_t smem = (size_t)(XR + AR) * P * 4;
+};
+
+__device__ __forceinline__ float4 fma4(float s, const float4& x, const float4& acc) {
+    return make_float4(fmaf(s, x.x, acc.x), fmaf(s, x.y, acc.y), fmaf(s, x.z, acc.z), fmaf(s, x.w, acc.w));
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) aa_act_kernel(AaArgs a) {
+    // Work per element: 12 + 12 FIR taps and two SnakeBeta evaluations against 8 bytes of HBM traffic: on B200 the kernel is
+    // bound by instruction issue, not by HBM (~37 instructions per 8 bytes is the balance point).  A thread owns 4
+    // channels (128-bit shared-memory accesses) and strips of 4 consecutive rows, so the FIR windows slide through
+    // registers: 10 loads per 8 up-sampled rows and 18 per 4 output rows instead of 6 and 12 per row.
+    using L = AaLayout<C>;
+    constexpr int TT = L::TT, S1 = L::S1, XR = L::XR, P = L::P, C4 = C / 4, RS = 256 / C4;
+    extern __shared__ __align__(16) float aa_sm[];
+    float* xs = aa_sm;
+    float* as = aa_sm + XR * P;
+    const int tid = threadIdx.x, c = 4 * (tid % C4), r0 = tid / C4;
+    const int b = blockIdx.y, t0 = blockIdx.x * TT, n = a.n;
+    const size_t boff = (size_t)b * n * C;
+    const bool interior = t0 - 6 >= 0 && t0 - 6 + XR <= n;           // no replicate padding inside this tile
+    for (int r = r0; r < XR; r += RS) {
+        int t = t0 - 6 + r;
+        if (!interior) t = t < 0 ? 0 : (t > n - 1 ? n - 1 : t);      // replicate padding of x
+        const size_t o = boff + (size_t)t * C + c;
+        float4 v = __ldg(reinterpret_cast<const float4*>(a.in_p[0] + o));
+        if (a.n_parts == 3) {
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.in_p[1] + o));
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(a.in_p[2] + o));
+            v.x = ((v.x + v1.x) + v2.x) / 3.0f; v.y = ((v.y + v1.y) + v2.y) / 3.0f;
+            v.z = ((v.z + v1.z) + v2.z) / 3.0f; v.w = ((v.w + v1.w) + v2.w) / 3.0f;
+        }
+        *reinterpret_cast<float4*>(xs + r * P + c) = v;
+    }
+    __syncthreads();
+    const float4 ea = __ldg(reinterpret_cast<const float4*>(a.ea + c)), ieb = __ldg(reinterpret_cast<const float4*>(a.ieb + c));
+    for (int s = r0; s < S1; s += RS) {
+        // positions t = t0 - 3 + 4 s + j (j = 0..3) need x[t - 3 .. t + 3]: rows 4 s .. 4 s + 9 of xs
+        float4 x[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) x[q] = *reinterpret_cast<const float4*>(xs + (4 * s + q) * P + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 ue = make_float4(0.f, 0.f, 0.f, 0.f), uo = ue;    // x[t + d] = x[j + 3 + d]
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                ue = fma4(2.0f * a.fu[2 * q + 1], x[j + 5 - q], ue); // u[2t]   = 2 sum f[2q+1] x[t + 2 - q]
+                uo = fma4(2.0f * a.fu[2 * q], x[j + 6 - q], uo);     // u[2t+1] = 2 sum f[2q]   x[t + 3 - q]
+            }
+            *reinterpret_cast<float4*>(as + (8 * s + 2 * j) * P + c) =
+                make_float4(snake_fast(ue.x, ea.x, ieb.x), snake_fast(ue.y, ea.y, ieb.y), snake_fast(ue.z, ea.z, ieb.z),
+                            snake_fast(ue.w, ea.w, ieb.w));
+            *reinterpret_cast<float4*>(as + (8 * s + 2 * j + 1) * P + c) =
+                make_float4(snake_fast(uo.x, ea.x, ieb.x), snake_fast(uo.y, ea.y, ieb.y), snake_fast(uo.z, ea.z, ieb.z),
+                            snake_fast(uo.w, ea.w, ieb.w));
+        }
+    }
+    __syncthreads();
+    const int abase = 2 * t0 - 6;                                    // doubled-rate index of as row 0
+    for (int s = r0; s < TT / 4; s += RS) {
+        const int t = t0 + 4 * s;
+        if (t >= n) break;
+        float4 av[18];                                               // a[2t - 5 .. 2t + 12]
+        if (interior) {
+#pragma unroll
+            for (int q = 0; q < 18; ++q) av[q] = *reinterpret_cast<const float4*>(as + (8 * s + 1 + q) * P + c);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 18; ++q) {
+                int i = 2 * t - 5 + q;
+                i = i < 0 ? 0 : (i > 2 * n - 1 ? 2 * n - 1 : i);     // replicate padding of a
+                av[q] = *reinterpret_cast<const float4*>(as + (i - abase) * P + c);
+            }
+        }
+        float* dst = a.out + boff + (size_t)t * C + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (t + j >= n) break;
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) y = fma4(a.fd[k], av[2 * j + k], y);
+            *reinterpret_cast<float4*>(dst + j * C) = y;
+        }
+    }
+}
+
+// One causal dilated Conv1d over channel-last rows on the tensor cores (split bf16, mma.sync): out = conv(in) + bias (+ res).
+struct ConvArgs {
+    const float* in;        // [B, n, C]
+    const uint2* wh;        // fragment-packed weights (hi / lo), as for the streaming kernels
+    const uint2* wl;
+    const float* bias;
+    const float* res;       // residual [B, n, C] or null; may alias out
+    float* out;
+    int n, d;
+};
+
+template <int C, int K>
+__global__ void __launch_bounds__(256) conv_cl_kernel(ConvArgs a) {
+    constexpr int TT = 128, PW = RowLayout<C>::PW, NT = C / 8;
+    extern __shared__ __align__(16) uint32_t conv_sm[];
+    const int lead = (K - 1) * a.d, rows = lead + TT;
+    uint32_t* sh = conv_sm;
+    uint32_t* sl = conv_sm + ((K - 1) * 5 + TT + 16) * PW;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int b = blockIdx.y, t0 = blockIdx.x * TT;
+    const size_t boff = (size_t)b * a.n * C;
+    constexpr int V = C / 2;
+    for (int i = tid; i < (rows + 16) * V; i += 256) {
+        const int r = i / V, cp = i - r * V;
+        const int t = t0 - lead + r;
+        float2 v = make_float2(0.f, 0.f);                            // causal zero padding (models.py:110,117); spare rows zero
+        if (r < rows && t >= 0 && t < a.n) v = __ldg(reinterpret_cast<const float2*>(a.in + boff + (size_t)t * C) + cp);
+        uint32_t hi, lo;
+        split_pair(v.x, v.y, hi, lo);
+        sh[r * PW + cp] = hi;
+        sl[r * PW + cp] = lo;
+    }
+    __syncthreads();
+    float2 bv[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) bv[nt] = __ldg(reinterpret_cast<const float2*>(a.bias + nt * 8 + 2 * (tid & 3)));
+    const uint32_t sh_a = (uint32_t)__cvta_generic_to_shared(sh), sl_a = (uint32_t)__cvta_generic_to_shared(sl);
+    mma_rows<C, C, K, 1>(sh_a, sl_a, lead, a.wh, a.wl, a.d, warp * 16, [&](int row, int nt, int co, float v0, float v1) {
+        const int t = t0 + row;
+        if (t < a.n) {
+            const size_t o = boff + (size_t)t * C + co;
+            float2 r = make_float2(0.f, 0.f);
+            if (a.res) r = *reinterpret_cast<const float2*>(a.res + o);
+            *reinterpret_cast<float2*>(a.out + o) = make_float2(v0 + bv[nt].x + r.x, v1 + bv[nt].y + r.y);
+        }
+    });
+}
+
+template <int C>
+int launch_aa_act(const AaArgs& a, int B, cudaStream_t stream) {
+    using L = AaLayout<C>;
+    static bool attr = false;
+    if (!attr) {
+        BVC_CUDA(cudaFuncSetAttribute(aa_act_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem));
+        attr = true;
+    }
+    aa_act_kernel<C><<<dim3((a.n + L::TT - 1) / L::TT, B), 256, L::smem, stream>>>(a);
+    BVC_CHECK_LAUNCH();
+    return BVC_OK;
+}
+static int launch_aa_act_c(int C, const AaArgs& a, int B, cudaStream_t stream) {
+    switch (C) {
+        case 64: return launch_aa_act<64>(a, B, stream);
+        case 32: return launch_aa_act<32>(a, B, stream);
+        case 16: return launch_aa_act<16>(a, B, stream);
+        default: return launch_aa_act<8>(a, B, stream);
+    }
+}
+
+template <int C, int K>
+int launch_conv_cl(const ConvArgs& a, int B, cudaStream_t stream) {
+    constexpr int TT = 128;
+    constexpr size_t smem = 2 * (size_t)((K - 1) * 5 + TT + 16) * RowLayout<C>::PW * 4;
+    static bool attr = false;
+    if (!attr) {
+        BVC_CUDA(cudaFuncSetAttribute(conv_cl_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    conv_cl_kernel<C, K><<<dim3((a.n + TT - 1) / TT, B), 256, smem, stream>>>(a);
+    BVC_CHECK_LAUNCH();
+    return BVC_OK;
+}
+template <int C>
+int launch_conv_cl_k(int K, const ConvArgs& a, int B, cudaStream_t stream) {
+    switch (K) {
+        case 3: return launch_conv_cl<C, 3>(a, B, stream);
+        case 7: return launch_conv_cl<C, 7>(a, B, stream);
+        case 11: return launch_conv_cl<C, 11>(a, B, stream);
+        default: set_error("vocoder: unsupported resblock kernel size"); return BVC_ERR_INVALID;
+    }
+}
+static int launch_conv_cl_ck(int C, int K, const ConvArgs& a, int B, cudaStream_t stream) {
+    switch (C) {
+        case 64: return launch_conv_cl_k<64>(K, a, B, stream);
+        case 32: return launch_conv_cl_k<32>(K, a, B, stream);
+        case 16: return launch_conv_cl_k<16>(K, a, B, stream);
+        default: return launch_conv_cl_k<8>(K, a, B, stream);
+    }
+}
+
 struct PostArgs {
     int n_parts;            // 3: mean of three partial tensors, 1: a single tensor
     const float* in_p[3];   // [B, n, C] channel-last
     int n;
     int n_out;              // min(length, n)
+    int skip_act;           // 1: the input is already activated (anti-aliased activation_post ran as its own kernel)
     const float* ea;
     const float* ieb;
     const float* w;         // [ci][7]
@@ -1183,7 +1401,7 @@ __global__ void __launch_bounds__(kThreads) post_kernel(PostArgs a) {
             const size_t o = boff + (size_t)tg * C + c;
             const float x = a.n_parts == 1 ? __ldg(a.in_p[0] + o)
                                            : ((__ldg(a.in_p[0] + o) + __ldg(a.in_p[1] + o)) + __ldg(a.in_p[2] + o)) / 3.0f;
-            v = snake(x, __ldg(a.ea + c), __ldg(a.ieb + c));
+            v = a.skip_act ? x : snake(x, __ldg(a.ea + c), __ldg(a.ieb + c));
         }
         s[c][p] = v;
     }
@@ -1281,6 +1499,7 @@ size_t vocoder_workspace_floats(const VocoderWeights& w, int B, int T) {
         total += 3 * ((size_t)B * C[i + 1] * n[i + 1] + 64);
         x0 = std::max(x0, (size_t)B * C[i + 1] * n[i + 1] + (size_t)512 * C[i + 1] + 64);
     }
+    if (w.antialias[0] || w.antialias[1] || w.antialias[2] || w.antialias[3] || w.antialias_post) total += 2 * (x0 + 64);
     return total + x0;
 }
 
@@ -1302,6 +1521,11 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
         size_t x0 = 0;
         for (int i = 0; i < 4; ++i) x0 = std::max(x0, (size_t)B * vb.C[i + 1] * vb.n[i + 1] + (size_t)512 * vb.C[i + 1]);
         vb.x0 = ws.take(x0);
+        vb.aa_a = vb.aa_b = nullptr;
+        if (w.antialias[0] || w.antialias[1] || w.antialias[2] || w.antialias[3] || w.antialias_post) {
+            vb.aa_a = ws.take(x0);
+            vb.aa_b = ws.take(x0);
+        }
     }
 
     {
@@ -1323,34 +1547,73 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
     // mma.sync kernel at C = 32, on par at 16, behind at 8 where the per-job epilogue latency dominates.  Default: stage 1.
     static const int umma_mask = getenv("BVC_VOC_UMMA") ? atoi(getenv("BVC_VOC_UMMA")) : 0x7;
     bool single[4] = {false, false, false, false};     // stage i wrote one tensor (the mean) instead of three partials
+    // ConvTranspose1d of stage i (reads the previous stage's partials or their mean) -> vb.x0
+    auto run_upsample = [&](int i) -> int {
+        UpsampleArgs up;
+        if (i == 0) {
+            up.n_parts = 1;
+            up.in_p[0] = up.in_p[1] = up.in_p[2] = vb.pre;
+            up.in_bstride = (long long)(T + 6) * w.c0;
+        } else {
+            up.n_parts = single[i - 1] ? 1 : 3;
+            for (int q = 0; q < 3; ++q) up.in_p[q] = vb.part[i - 1][single[i - 1] ? 0 : q];
+            up.in_bstride = (long long)vb.n[i] * vb.C[i];
+        }
+        up.n_in = (int)vb.n[i];
+        up.n_out = (int)vb.n[i + 1];
+        up.b_up = w.b_up[i];
+        up.upf_h = w.upf_h[i];
+        up.upf_l = w.upf_l[i];
+        up.x0 = vb.x0;
+        int rc;
+        switch (vb.C[i + 1]) {
+            case 64: rc = launch_upsample<64, 8>(up, B, stream); break;
+            case 32: rc = launch_upsample<32, 8>(up, B, stream); break;
+            case 16: rc = launch_upsample<16, 2>(up, B, stream); break;
+            default: rc = launch_upsample<8, 2>(up, B, stream); break;
+        }
+        return rc;
+    };
     for (int i = 0; i < 4; ++i) {
+        if (w.antialias[i]) {
+            // Anti-aliased stage, layer by layer: transposed conv, then per resblock 3 x (Activation1d, dilated conv,
+            // Activation1d, conv + residual).  Always split-bf16 tensor-core convolutions, whatever `precision` says.
+            { const int rc_up = run_upsample(i); if (rc_up != BVC_OK) return rc_up; }
+            const int Cc = vb.C[i + 1], nn = (int)vb.n[i + 1];
+            for (int jj = 0; jj < 3; ++jj) {
+                const int j = 2 - jj;
+                const AmpBlockWeights& bw = w.blocks[i * 3 + j];
+                const float* cur = vb.x0;
+                for (int l = 0; l < 3; ++l) {
+                    AaArgs aa;
+                    aa.n_parts = 1; aa.n = nn;
+                    for (int q = 0; q < 12; ++q) { aa.fu[q] = w.aa_up[q]; aa.fd[q] = w.aa_down[q]; }
+                    ConvArgs cv;
+                    cv.n = nn;
+                    // xt = c1(a1(x))
+                    aa.in_p[0] = aa.in_p[1] = aa.in_p[2] = cur;
+                    aa.ea = bw.act[2 * l].ea; aa.ieb = bw.act[2 * l].inv_eb; aa.out = vb.aa_a;
+                    BVC_TRY(launch_aa_act_c(Cc, aa, B, stream));
+                    cv.in = vb.aa_a; cv.wh = bw.f1h[l]; cv.wl = bw.f1l[l]; cv.bias = bw.b1[l]; cv.res = nullptr; cv.out = vb.aa_b;
+                    cv.d = w.dil[l];
+                    BVC_TRY(launch_conv_cl_ck(Cc, bw.k, cv, B, stream));
+                    // x = c2(a2(xt)) + x
+                    aa.in_p[0] = aa.in_p[1] = aa.in_p[2] = vb.aa_b;
+                    aa.ea = bw.act[2 * l + 1].ea; aa.ieb = bw.act[2 * l + 1].inv_eb;
+                    BVC_TRY(launch_aa_act_c(Cc, aa, B, stream));
+                    cv.in = vb.aa_a; cv.wh = bw.f2h[l]; cv.wl = bw.f2l[l]; cv.bias = bw.b2[l]; cv.res = cur; cv.out = vb.part[i][j];
+                    cv.d = 1;
+                    BVC_TRY(launch_conv_cl_ck(Cc, bw.k, cv, B, stream));
+                    cur = vb.part[i][j];
+                }
+            }
+            continue;
+        }
         if (precision >= 1 && ((umma_mask >> i) & 1) && w.umma[i].ready) {
             // tcgen05 stage kernel: C <= 32: all three resblocks per CTA, the output is their mean; C = 64: one resblock per CTA
             const bool all_chains = vb.C[i + 1] <= 32;
-            UpsampleArgs up;
-            if (i == 0) {
-                up.n_parts = 1;
-                up.in_p[0] = up.in_p[1] = up.in_p[2] = vb.pre;
-                up.in_bstride = (long long)(T + 6) * w.c0;
-            } else {
-                up.n_parts = single[i - 1] ? 1 : 3;
-                for (int q = 0; q < 3; ++q) up.in_p[q] = vb.part[i - 1][single[i - 1] ? 0 : q];
-                up.in_bstride = (long long)vb.n[i] * vb.C[i];
-            }
-            up.n_in = (int)vb.n[i];
-            up.n_out = (int)vb.n[i + 1];
-            up.b_up = w.b_up[i];
-            up.upf_h = w.upf_h[i];
-            up.upf_l = w.upf_l[i];
-            up.x0 = vb.x0;
+            { const int rc_up = run_upsample(i); if (rc_up != BVC_OK) return rc_up; }
             int rc;
-            switch (vb.C[i + 1]) {
-                case 64: rc = launch_upsample<64, 8>(up, B, stream); break;
-                case 32: rc = launch_upsample<32, 8>(up, B, stream); break;
-                case 16: rc = launch_upsample<16, 2>(up, B, stream); break;
-                default: rc = launch_upsample<8, 2>(up, B, stream); break;
-            }
-            if (rc != BVC_OK) return rc;
             UmmaStageArgs ua;
             ua.x0 = vb.x0;
             ua.n_out = (int)vb.n[i + 1];
@@ -1438,6 +1701,18 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
         for (int q = 0; q < 3; ++q) p.in_p[q] = vb.part[3][q];
         p.n = (int)vb.n[4];
         p.n_out = length < p.n ? length : p.n;
+        p.skip_act = 0;
+        if (w.antialias_post) {     // Activation1d(activation_post) as its own kernel (models.py:189-190,228), then conv_post + tanh
+            AaArgs aa;
+            aa.n_parts = p.n_parts; aa.n = p.n;
+            for (int q = 0; q < 3; ++q) aa.in_p[q] = p.in_p[q];
+            for (int q = 0; q < 12; ++q) { aa.fu[q] = w.aa_up[q]; aa.fd[q] = w.aa_down[q]; }
+            aa.ea = w.act_post.ea; aa.ieb = w.act_post.inv_eb; aa.out = vb.aa_a;
+            BVC_TRY(launch_aa_act_c(8, aa, B, stream));
+            p.n_parts = 1;
+            p.in_p[0] = p.in_p[1] = p.in_p[2] = vb.aa_a;
+            p.skip_act = 1;
+        }
         p.ea = w.act_post.ea;
         p.ieb = w.act_post.inv_eb;
         p.w = w.w_post;

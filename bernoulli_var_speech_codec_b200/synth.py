@@ -66,8 +66,37 @@ def _wn_conv(gen, sd, name, d0, d1, k, fan_in):
     sd[f"{name}.weight_v"] = v
 
 
+def kaiser_sinc_filter(cutoff: float, half_width: float, kernel_size: int) -> torch.Tensor:
+    """The low-pass FIR of the anti-aliased activation, [1, 1, kernel_size] (restates
+    third_party/BigVGAN/alias_free_torch/filter.py:28-59: Kaiser-windowed sinc, normalised to unit DC gain).
+    The reference registers it as a buffer, so it travels in the checkpoint; tests pin this restatement against the
+    reference's own values (tests/golden/aa_filter.npz)."""
+    half = kernel_size // 2
+    delta_f = 4 * half_width
+    A = 2.285 * (half - 1) * math.pi * delta_f + 7.95
+    beta = 0.1102 * (A - 8.7) if A > 50.0 else (0.5842 * (A - 21) ** 0.4 + 0.07886 * (A - 21.0) if A >= 21.0 else 0.0)
+    window = torch.kaiser_window(kernel_size, beta=beta, periodic=False)
+    time = (torch.arange(-half, half) + 0.5) if kernel_size % 2 == 0 else (torch.arange(kernel_size) - half)
+    f = 2 * cutoff * window * torch.sinc(2 * cutoff * time)
+    return (f / f.sum()).view(1, 1, kernel_size)
+
+
 def synth_vocoder_state_dict(seed: int = 2, vcfg: dict | None = None):
+    """vcfg keys layers_antialias / antialias_post switch the activation entries to the reference's Activation1d schema
+    (`.act.alpha`, `.act.beta` + the `upsample.filter` / `downsample.lowpass.filter` buffers; models.py:66-88,180-190)."""
     vcfg = vcfg or {}
+    aa_layers = list(vcfg.get("layers_antialias", [False] * 4))
+    aa_post = bool(vcfg.get("antialias_post", False))
+    aa_filter = kaiser_sinc_filter(0.25, 0.3, 12)       # Activation1d defaults: ratio 2, 12 taps (act.py:10-15, resample.py:17-19)
+
+    def act_entries(sd, name, ch, gen, aa):
+        inner = name + (".act" if aa else "")
+        sd[inner + ".alpha"] = 0.5 * torch.randn(ch, generator=gen)
+        sd[inner + ".beta"] = 0.5 * torch.randn(ch, generator=gen)
+        if aa:
+            sd[name + ".upsample.filter"] = aa_filter.clone()
+            sd[name + ".downsample.lowpass.filter"] = aa_filter.clone()
+
     num_mels = vcfg.get("num_mels", 80)
     c0 = vcfg.get("upsample_initial_channel", 128)
     rates = vcfg.get("upsample_rates", [8, 8, 2, 2])
@@ -91,10 +120,8 @@ def synth_vocoder_state_dict(seed: int = 2, vcfg: dict | None = None):
                     _wn_conv(gen, sd, f"resblocks.{n}.{grp}.{l}", ch, ch, rk, ch * rk)
                     sd[f"resblocks.{n}.{grp}.{l}.bias"] = _uniform(gen, (ch,), 1.0 / math.sqrt(ch * rk))
             for a in range(6):
-                sd[f"resblocks.{n}.activations.{a}.alpha"] = 0.5 * torch.randn(ch, generator=gen)
-                sd[f"resblocks.{n}.activations.{a}.beta"] = 0.5 * torch.randn(ch, generator=gen)
-    sd["activation_post.alpha"] = 0.5 * torch.randn(ch, generator=gen)
-    sd["activation_post.beta"] = 0.5 * torch.randn(ch, generator=gen)
+                act_entries(sd, f"resblocks.{n}.activations.{a}", ch, gen, aa_layers[i])
+    act_entries(sd, "activation_post", ch, gen, aa_post)
     _wn_conv(gen, sd, "conv_post", 1, ch, 7, ch * 7)
     sd["conv_post.bias"] = _uniform(gen, (1,), 1.0 / math.sqrt(ch * 7))
     return sd
@@ -105,8 +132,12 @@ def write_synthetic_checkpoints(out_dir: str, seed: int = 1, sharpen: float = 30
     """Writes ``bvrnn_synth_s{seed}`` and ``vocoder_synth_s{seed}`` into out_dir; returns their paths."""
     os.makedirs(out_dir, exist_ok=True)
     tag = f"s{seed}_k{sharpen:g}_g{gain:g}"
+    vtag = ""
+    if vcfg and (any(vcfg.get("layers_antialias", [])) or vcfg.get("antialias_post", False)):
+        vtag = "_aa" + "".join("1" if a else "0" for a in vcfg.get("layers_antialias", [False] * 4)) + \
+               ("p" if vcfg.get("antialias_post", False) else "")
     p1 = os.path.join(out_dir, f"bvrnn_synth_{tag}")
-    p2 = os.path.join(out_dir, f"vocoder_synth_{tag}")
+    p2 = os.path.join(out_dir, f"vocoder_synth_{tag}{vtag}")
     if force or not os.path.exists(p1):
         tmp = p1 + f".tmp{os.getpid()}"
         torch.save({"vrnn": synth_bvrnn_state_dict(seed, sharpen=sharpen, gain=gain)}, tmp)

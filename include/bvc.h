@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BVC_ABI_VERSION 1
+#define BVC_ABI_VERSION 2
 
 typedef enum bvc_status {
     BVC_OK = 0,
@@ -66,6 +66,12 @@ typedef struct bvc_config {
     int32_t voc_num_kernels;           /* 3                                            */
     int32_t voc_res_kernels[3];        /* 3,7,11                                       */
     int32_t voc_res_dilations[3];      /* 1,3,5 (same for every resblock)              */
+    /* ABI 2: anti-aliased activations (third_party/BigVGAN/models.py:66-88,172-190; alias_free_torch/act.py:8-28).
+     * A stage with voc_antialias[i] = 1 expects the Activation1d checkpoint schema for its resblocks
+     * (activations.N.act.alpha / .act.beta / .upsample.filter / .downsample.lowpass.filter) and runs layer by layer
+     * (FIR up -> SnakeBeta -> FIR down fused in one shared-memory kernel); both shipped configs leave these 0. */
+    int32_t voc_antialias[4];          /* vocoder_config.layers_antialias               */
+    int32_t voc_antialias_post;        /* vocoder_config.antialias_post                 */
 } bvc_config;
 
 /* One named checkpoint tensor, float32, contiguous, in HOST memory. */

@@ -173,6 +173,25 @@ def _snakebeta(x, alpha, beta):
     return x + (1.0 / (b + 1e-9)) * torch.sin(x * a) ** 2
 
 
+def _aa_snakebeta(x, alpha, beta, f_up, f_down):
+    """Anti-aliased activation (reference alias_free_torch/act.py:23-28): 2x FIR up-sampling (resample.py:24-32:
+    replicate pad 5|5, transposed conv with the 12-tap Kaiser-sinc filter, x2 gain, crop 15|15), SnakeBeta at the doubled
+    rate, 2x FIR down-sampling (resample.py:46-48 -> filter.py:88-96: replicate pad 5|6, strided depthwise conv).
+    The filters are the checkpoint's registered buffers, as in the reference."""
+    C = x.shape[1]
+    k = f_up.shape[-1]
+    pad = k // 2 - 1
+    pad_l = pad * 2 + (k - 2) // 2
+    pad_r = pad * 2 + (k - 2 + 1) // 2
+    u = F.pad(x, (pad, pad), mode="replicate")
+    u = 2 * F.conv_transpose1d(u, f_up.expand(C, -1, -1), stride=2, groups=C)
+    u = u[..., pad_l:-pad_r]
+    a = _snakebeta(u, alpha, beta)
+    kd = f_down.shape[-1]
+    a = F.pad(a, (kd // 2 - int(kd % 2 == 0), kd // 2), mode="replicate")
+    return F.conv1d(a, f_down.expand(C, -1, -1), stride=2, groups=C)
+
+
 def _cconv(x, w, b, dilation=1):
     k = w.shape[2]
     return F.conv1d(F.pad(x, ((k - 1) * dilation, 0)), w, b, dilation=dilation)
@@ -180,10 +199,11 @@ def _cconv(x, w, b, dilation=1):
 
 class VocoderOracle:
     def __init__(self, sd, vcfg):
-        if vcfg.get("activation", "snakebeta") != "snakebeta" or any(vcfg.get("layers_antialias", [])) \
-                or vcfg.get("antialias_post", False) or any(vcfg.get("layers_sym", [])) \
+        if vcfg.get("activation", "snakebeta") != "snakebeta" or any(vcfg.get("layers_sym", [])) \
                 or vcfg.get("pre_sym", False) or vcfg.get("post_sym", False):
-            raise NotImplementedError("oracle covers the shipped causal snakebeta configuration only")
+            raise NotImplementedError("oracle covers the causal snakebeta configurations only")
+        self.aa = [bool(a) for a in vcfg.get("layers_antialias", [False] * len(vcfg["upsample_rates"]))]
+        self.aa_post = bool(vcfg.get("antialias_post", False))
         self.rates = list(vcfg["upsample_rates"])
         self.rks = list(vcfg["resblock_kernel_sizes"])
         self.dil = [list(d) for d in vcfg["resblock_dilation_sizes"]]
@@ -194,18 +214,27 @@ class VocoderOracle:
         for n in range(len(self.rates) * len(self.rks)):
             c1 = [(f(f"resblocks.{n}.convs1.{l}"), sd[f"resblocks.{n}.convs1.{l}.bias"]) for l in range(3)]
             c2 = [(f(f"resblocks.{n}.convs2.{l}"), sd[f"resblocks.{n}.convs2.{l}.bias"]) for l in range(3)]
-            act = [(sd[f"resblocks.{n}.activations.{a}.alpha"], sd[f"resblocks.{n}.activations.{a}.beta"])
-                   for a in range(6)]
+            act = [self._act(sd, f"resblocks.{n}.activations.{a}", self.aa[n // len(self.rks)]) for a in range(6)]
             self.blocks.append((c1, c2, act))
-        self.act_post = (sd["activation_post.alpha"], sd["activation_post.beta"])
+        self.act_post = self._act(sd, "activation_post", self.aa_post)
         self.post = (f("conv_post"), sd["conv_post.bias"])
+
+    @staticmethod
+    def _act(sd, name, aa):
+        """-> callable activation; Activation1d wraps SnakeBeta as `.act` and owns two filter buffers (models.py:66-88)."""
+        if not aa:
+            alpha, beta = sd[name + ".alpha"], sd[name + ".beta"]
+            return lambda x: _snakebeta(x, alpha, beta)
+        alpha, beta = sd[name + ".act.alpha"], sd[name + ".act.beta"]
+        f_up, f_down = sd[name + ".upsample.filter"], sd[name + ".downsample.lowpass.filter"]
+        return lambda x: _aa_snakebeta(x, alpha, beta, f_up, f_down)
 
     def _amp(self, n, x):
         c1, c2, act = self.blocks[n]
         d = self.dil[n % len(self.rks)]
         for l in range(3):                                            # models.py:103-121
-            xt = _cconv(_snakebeta(x, *act[2 * l]), *c1[l], dilation=d[l])
-            xt = _cconv(_snakebeta(xt, *act[2 * l + 1]), *c2[l])
+            xt = _cconv(act[2 * l](x), *c1[l], dilation=d[l])
+            xt = _cconv(act[2 * l + 1](xt), *c2[l])
             x = xt + x
         return x
 
@@ -226,7 +255,7 @@ class VocoderOracle:
             x = acc / nk                                              # :219-225
             if taps is not None:
                 taps[f"stage{i}"] = x
-        x = _snakebeta(x, *self.act_post)
+        x = self.act_post(x)
         x = torch.tanh(_cconv(x, *self.post))                         # :228-236
         return x[:, :, :length]                                       # :238
 

@@ -15,6 +15,9 @@ Fixtures (all float32 unless noted):
   synth_var_small.npz   var-bitrate, B=2, L=5000+odd, bitrates 3000 -> 35 bits
   synth_fix_small.npz   fixed 64-bit config
   synth_var_bits.npz    bit budget edge cases 0 / 1 / 64 / >64 on one short clip
+  synth_var_aa_small.npz  configs/config_varBitRate_antialias.toml (anti-aliased activations in every stage and
+                        before conv_post; checkpoint with the Activation1d schema): codes, dec_mel, wav
+  aa_filter.npz         the reference's 12-tap Kaiser-sinc filter (alias_free_torch/filter.py:28-59), pins synth.py's
   stim01_var.npz        BASELINE config #1 input (MUSHRA stim_01 ref.wav, CC BY 4.0,
                         resampled 24k->22.05k, peak-normalised) at 3000 bps
 """
@@ -93,6 +96,16 @@ def main():
 
     m_fix = ref.BVRNNCodecModel(cfg_fix, p_b, p_v).eval()
     save("synth_fix_small.npz", run_reference(ref, m_fix, x, 3000), bitrate=3000, **meta)
+
+    # anti-aliased activations (dead under the shipped configs; switchable, models.py:82-88,189-190)
+    import toml
+    cfg_aa = os.path.join(ROOT, "configs", "config_varBitRate_antialias.toml")
+    _, p_v_aa = write_synthetic_checkpoints(CKPT_DIR, seed=SEED, sharpen=SHARPEN, vcfg=toml.load(cfg_aa)["vocoder_config"])
+    m_aa = ref.BVRNNCodecModel(cfg_aa, p_b, p_v_aa).eval()
+    r = run_reference(ref, m_aa, x, 3000)
+    save("synth_var_aa_small.npz", dict(x=r["x"], codes=r["codes"], dec_mel=r["dec_mel"], wav=r["wav"]), bitrate=3000, **meta)
+    filt = sys.modules["third_party.BigVGAN.alias_free_torch.filter"].kaiser_sinc_filter1d(0.25, 0.3, 12)
+    save("aa_filter.npz", dict(filter=filt.flatten()), cutoff=0.25, half_width=0.3, kernel_size=12)
 
     # BASELINE config #1 input (reference example.py:12-17; soundfile absent -> scipy.io.wavfile)
     import scipy.io.wavfile

@@ -31,6 +31,27 @@ def cfg_fix():
 
 
 @pytest.fixture(scope="session")
+def cfg_aa():
+    """config_varBitRate with the anti-aliased activations on (vocoder_config.layers_antialias / antialias_post)."""
+    return os.path.join(ROOT, "configs", "config_varBitRate_antialias.toml")
+
+
+@pytest.fixture(scope="session")
+def ckpts_aa(ckpts, cfg_aa):
+    """Same BVRNN checkpoint; vocoder checkpoint with the reference's Activation1d schema."""
+    import toml
+    from bernoulli_var_speech_codec_b200.synth import write_synthetic_checkpoints
+    d = os.environ.get("BVC_CKPT_DIR", "/tmp/bvc_ckpts")
+    return write_synthetic_checkpoints(d, seed=1, sharpen=30.0, vcfg=toml.load(cfg_aa)["vocoder_config"])
+
+
+@pytest.fixture(scope="session")
+def oracle_aa(ckpts_aa, cfg_aa):
+    from oracle.codec_oracle import OracleCodec
+    return OracleCodec(cfg_aa, *ckpts_aa)
+
+
+@pytest.fixture(scope="session")
 def oracle_var(ckpts, cfg_var):
     from oracle.codec_oracle import OracleCodec
     return OracleCodec(cfg_var, *ckpts)
@@ -63,6 +84,12 @@ def model_fix(request, ckpts, cfg_fix):
     m._engine.set_precision(request.param)
     m.precision = request.param
     return m
+
+
+@pytest.fixture(scope="session")
+def model_aa(ckpts_aa, cfg_aa):
+    from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
+    return BVRNNCodecModel(cfg_aa, *ckpts_aa).eval()
 
 
 def golden(name):

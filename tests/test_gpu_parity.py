@@ -223,6 +223,29 @@ def test_fused_forward(model_var, model_fix, oracle_var):
     assert _snr_db(ref, model_var(x.to(model_var.device), 3000).cpu()) >= 60.0
 
 
+def test_antialiased_activation_path(model_aa, oracle_aa):
+    """vocoder_config.layers_antialias / antialias_post = true (Activation1d: FIR up -> SnakeBeta -> FIR down, fused in one
+    shared-memory kernel; stages run layer by layer): golden vector of the unmodified reference, then the oracle on a
+    longer ragged batch (several tiles per stage, replicate padding at both utterance edges)."""
+    g = golden("synth_var_aa_small.npz")
+    dev = model_aa.device
+    x = torch.from_numpy(g["x"]).to(dev)
+    codes = model_aa.encode(x, float(g["bitrate"]))
+    assert np.array_equal(codes.cpu().numpy(), g["codes"])
+    wav = model_aa.decode(torch.from_numpy(g["codes"]).to(dev), x.shape[1]).cpu().numpy()
+    assert wav.shape == g["wav"].shape and snr_db(g["wav"], wav) >= 60.0
+    # bare vocoder against the oracle: (B, 80, T) -> (B, 1, length)
+    gen = torch.Generator().manual_seed(21)
+    mel = -5.0 + 2.0 * torch.randn(3, 80, 37, generator=gen)
+    w_o = oracle_aa.vocoder(mel, 37 * 256 + 100)
+    w = model_aa.vocoder(mel.to(dev), 37 * 256 + 100).cpu()
+    assert w.shape == w_o.shape and snr_db(w_o.numpy(), w.numpy()) >= 60.0
+    assert np.abs(w.numpy() - w_o.numpy()).max() <= 2e-3
+    # forward through the fused path too
+    xs = _noise(2, 9000, 5)
+    assert snr_db(oracle_aa.forward(xs, 3000).numpy(), model_aa(xs.to(dev), 3000).cpu().numpy()) >= 60.0
+
+
 def test_packed_wire_format_round_trip(model_var, model_fix, oracle_var):
     """encode_packed / decode_packed (uint64 per frame) reproduce the float-code path bit for bit, for every budget edge."""
     x = _noise(3, 9000, 77).to(model_var.device)

@@ -37,6 +37,27 @@ def test_oracle_bit_budget_edges(tag, nbits, oracle_var):
     assert np.abs(wav - g["wav"]).max() < 2e-5
 
 
+def test_oracle_antialiased_vocoder_matches_reference_golden(oracle_aa):
+    """Anti-aliased activations (Activation1d in every resblock and before conv_post): oracle == unmodified reference."""
+    g = golden("synth_var_aa_small.npz")
+    x = torch.from_numpy(g["x"])
+    assert np.array_equal(oracle_aa.encode(x, float(g["bitrate"])).numpy(), g["codes"])
+    taps = {}
+    wav = oracle_aa.decode(torch.from_numpy(g["codes"]), x.shape[1], taps)
+    assert np.abs(taps["dec_mel"].numpy() - g["dec_mel"]).max() < 5e-6
+    assert wav.shape == g["wav"].shape and np.abs(wav.numpy() - g["wav"]).max() < 2e-5
+    plain = golden("synth_var_small.npz")["wav"]                 # same codes path, different activations: must differ
+    assert np.abs(plain - g["wav"]).max() > 1e-3
+
+
+def test_antialias_filter_restatement():
+    """synth.kaiser_sinc_filter (written into synthetic checkpoints) == the reference's kaiser_sinc_filter1d values."""
+    from bernoulli_var_speech_codec_b200.synth import kaiser_sinc_filter
+    g = golden("aa_filter.npz")
+    f = kaiser_sinc_filter(float(g["cutoff"]), float(g["half_width"]), int(g["kernel_size"])).flatten().numpy()
+    assert np.array_equal(f, g["filter"])
+
+
 def test_oracle_rejects_short_input(oracle_var):
     with pytest.raises(RuntimeError):
         oracle_var.encode(torch.zeros(1, 512), 3000)
