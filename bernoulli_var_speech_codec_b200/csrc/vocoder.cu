@@ -251,6 +251,24 @@ __global__ void __launch_bounds__(kThreads, 1) stage_fp32_kernel(StageArgs a) {
 // context of each conv input: (K-1) d rows for the dilated conv of layer l, K-1 rows for its second conv.  Those
 // rows are kept in shared memory from one tile to the next (6 small context buffers), so no sample is ever
 // computed twice; a range that starts inside the utterance warms its contexts up on the 12 (K-1) samples before it.
+// Time ranges per utterance for the streaming stage kernels.  Every CTA walks one range tile by tile, all CTAs of a launch
+// take about the same time, and `slots` of them are resident at once, so the launch lasts ceil(CTAs / slots) waves of
+// (tiles per range + warm-up tiles) tile times: pick the range count that minimises that product (a launch of 5.2 waves
+// costs 6).  `units` = CTAs per range index (utterances x resblock CTAs).
+static int pick_ranges(int units, int tiles_total, int warm_tiles, int slots) {
+    int best = 1;
+    long long best_cost = -1;
+    const int max_ranges = tiles_total / (4 * (warm_tiles > 0 ? warm_tiles : 1)) > 0 ? tiles_total / (4 * (warm_tiles > 0 ? warm_tiles : 1)) : 1;
+    for (int r = 1; r <= max_ranges && r <= 64; ++r) {
+        const int tiles_per = (tiles_total + r - 1) / r;
+        const int r_eff = (tiles_total + tiles_per - 1) / tiles_per;
+        const long long waves = ((long long)units * r_eff + slots - 1) / slots;
+        const long long cost = waves * (tiles_per + (r_eff > 1 ? warm_tiles : 0));
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = r_eff; }
+    }
+    return best;
+}
+
 template <int C>
 struct RowLayout {
     static constexpr int PW = C >= 16 ? C / 2 + 4 : C / 2;   // uint32 (bf16 pair) words per activation row; rows are
@@ -1145,12 +1163,9 @@ int launch_stage_umma(const UmmaStageArgs& a, int B, cudaStream_t stream) {
     // time ranges per utterance: ~4 waves of CTAs, but ranges long enough that their warm-up (120 samples) stays small
     const int ctas_per_range = 3 / NCH;
     const int tiles_total = (a.n_out + UM_TT - 1) / UM_TT;
-    const int want = (4 * sms + B * ctas_per_range - 1) / (B * ctas_per_range);
-    const int max_ranges = tiles_total / 4 > 0 ? tiles_total / 4 : 1;
-    int ranges = want < max_ranges ? want : max_ranges;
-    if (ranges < 1) ranges = 1;
-    const int tiles_per = (tiles_total + ranges - 1) / ranges;
-    ranges = (tiles_total + tiles_per - 1) / tiles_per;
+    // one CTA per SM; with one resblock per CTA the three kinds of CTAs cost 11 : 7 : 3, which the wave model below only
+    // approximates (the heavy ones are launched first)
+    const int ranges = pick_ranges(B * ctas_per_range, tiles_total, (120 + UM_TT - 1) / UM_TT, sms);
     stage_umma_kernel<C, U, MT, NCH><<<dim3(ranges, B, ctas_per_range), L::threads, L::total, stream>>>(a);
     BVC_CHECK_LAUNCH();
     return BVC_OK;
@@ -1444,12 +1459,7 @@ int launch_stage(const StageArgs& a_in, int B, int precision, cudaStream_t strea
         // time ranges per utterance: enough CTAs for ~4 waves (tail effect), but ranges long enough that the
         // warm-up of a range (12 (K-1) samples) stays small against its length
         const int tiles_total = (a.n_out + TT - 1) / TT;
-        const int want = (4 * sms * ctas_per_sm + B - 1) / B;
-        const int max_ranges = tiles_total / (4 * ((HALO + TT - 1) / TT)) > 0 ? tiles_total / (4 * ((HALO + TT - 1) / TT)) : 1;
-        int ranges = want < max_ranges ? want : max_ranges;
-        if (ranges < 1) ranges = 1;
-        const int tiles_per = (tiles_total + ranges - 1) / ranges;
-        ranges = (tiles_total + tiles_per - 1) / tiles_per;
+        const int ranges = pick_ranges(B, tiles_total, (HALO + TT - 1) / TT, sms * ctas_per_sm);
         dim3 grid(ranges, B);
         stage_stream_kernel<C, U, K, MT><<<grid, kThreads, smem, stream>>>(a);
     } else {
