@@ -1437,7 +1437,7 @@ __global__ void __launch_bounds__(kThreads) post_kernel(PostArgs a) {
 // tile rows and m16 tiles per warp of the streaming tensor-core kernel, per channel count
 template <int C> struct StreamTile { static constexpr int TT = 128, MT = 1; };
 template <> struct StreamTile<16> { static constexpr int TT = 256, MT = 2; };
-template <> struct StreamTile<8> { static constexpr int TT = 512, MT = 2; };
+template <> struct StreamTile<8> { static constexpr int TT = 256, MT = 2; };
 
 template <int C, int U, int K>
 int launch_stage(const StageArgs& a_in, int B, int precision, cudaStream_t stream) {
