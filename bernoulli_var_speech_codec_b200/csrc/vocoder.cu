@@ -1042,17 +1042,10 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
         };
         auto c2_off = [&](int c, int K, int l) { return (c == 0 ? L::c2(0) : c == 1 ? L::c2(1) : L::c2(2)) + 2 * G * (K - 1) * l * 16; };
 
-        for (int tile = 0; tile < n_tiles; ++tile) {
-            const int t0 = t_first + tile * UM_TT;
-            if (et == 0) UM_TRACE(72);
-            // contexts of the first dilated convs (layer 0) in front of the tiles
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int K = um_K(kc0 + c);
-                restore(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, c1_off(c, K, 0), (K - 1) * 1);
-            }
-            um_wait(&x_full, tile & 1);
-            // ---- x of the resblocks = x0 (TMEM) and their first conv inputs ----
+        // Tile prologue of one resblock, second half: x = x0 row (TMEM, next to a zeroed aux accumulator), first conv
+        // input = SnakeBeta(x).  The first half (restore of the layer-0 context) must be separated from it by an epi_bar.
+        auto chain_begin = [&](int c) {
+            const int kc = kc0 + c, K = um_K(kc);
             float xr[CPT];
             const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -1060,26 +1053,39 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                 const float4 u = *reinterpret_cast<const float4*>(x0 + p * PX + CPT * ge + 4 * q);
                 xr[4 * q] = u.x; xr[4 * q + 1] = u.y; xr[4 * q + 2] = u.z; xr[4 * q + 3] = u.w;
             }
-            epi_bar();                                  // all context rows restored before this tile's tails replace them
-            if (lane == 0) um_arrive(&x_empty);         // the loader may fetch the next tile
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int kc = kc0 + c, K = um_K(kc);
-#pragma unroll
-                for (int s8 = 0; s8 < S8; ++s8) {
-                    um_st8(t_lane + c * 4 * N + CPT * ge + 8 * s8, xr + 8 * s8);
-                    um_st8(t_lane + c * 4 * N + N + CPT * ge + 8 * s8, zero8);      // the second convs accumulate onto [x | 0]
-                }
-                float ea[CPT], ieb[CPT], y[CPT];
-                loadc(a.ea[kc][0], ea);
-                loadc(a.ieb[kc][0], ieb);
-#pragma unroll
-                for (int i = 0; i < CPT; ++i) y[i] = snake_fast(xr[i], ea[i], ieb[i]);
-                write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, y, c1_off(c, K, 0), (K - 1) * 1);
-                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-                publish(c);
+            for (int s8 = 0; s8 < S8; ++s8) {
+                um_st8(t_lane + c * 4 * N + CPT * ge + 8 * s8, xr + 8 * s8);
+                um_st8(t_lane + c * 4 * N + N + CPT * ge + 8 * s8, zero8);      // the second convs accumulate onto [x | 0]
             }
+            float ea[CPT], ieb[CPT], y[CPT];
+            loadc(a.ea[kc][0], ea);
+            loadc(a.ieb[kc][0], ieb);
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) y[i] = snake_fast(xr[i], ea[i], ieb[i]);
+            write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, y, c1_off(c, K, 0), (K - 1) * 1);
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            publish(c);
+        };
+        auto chain_restore0 = [&](int c) {
+            const int K = um_K(kc0 + c);
+            restore(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, c1_off(c, K, 0), (K - 1) * 1);
+        };
 
+        // first tile: all resblocks start together.  Later tiles are started resblock by resblock from inside the previous
+        // tile's job loop (right after the resblock's last epilogue), so the tensor core never waits for a tile boundary.
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) chain_restore0(c);
+        um_wait(&x_full, 0);
+        epi_bar();                                      // all context rows restored before this tile's tails replace them
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) chain_begin(c);
+        __syncwarp();
+        if (lane == 0) um_arrive(&x_empty);             // the loader may fetch the next tile
+
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            const int t0 = t_first + tile * UM_TT;
+            if (et == 0) UM_TRACE(72);
             if (et == 0) UM_TRACE(73);
             float osum[CPT];
 #pragma unroll
@@ -1113,8 +1119,11 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                 } else {
                     // residual stream updated in TMEM: x_true = x + (sum of the second convs' biases so far)
                     const int ctx = (K - 1) * (l == 0 ? 3 : 5);
+                    const bool start_next = l == 2 && tile + 1 < n_tiles;     // this resblock is done with the tile
                     if (l < 2) restore(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, c1_off(c, K, l + 1), ctx);
+                    else if (start_next) chain_restore0(c);
                     tld(t_lane + c * 4 * N + CPT * ge, v);
+                    if (start_next && c == 0) um_wait(&x_full, (tile + 1) & 1);      // the next x0 tile (loaded during this one)
                     epi_bar();
                     if (l < 2) {
 #pragma unroll
@@ -1125,6 +1134,13 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
 #pragma unroll
                         for (int i = 0; i < CPT; ++i) osum[i] += v[i] + pa[i];
                         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                        if (start_next) {
+                            chain_begin(c);
+                            if (c == NCH - 1) {
+                                __syncwarp();
+                                if (lane == 0) um_arrive(&x_empty);
+                            }
+                        }
                     }
                 }
                 if (et == 0) UM_TRACE(ji * 4 + 3);
