@@ -606,8 +606,11 @@ template <int C, int U, int MT, int NCH>
 struct UmLayout {
     static constexpr int TT = UM_ROWS * MT;
     static constexpr int G = C / 8, N = C < 16 ? 16 : C, CIN = 2 * C;
-    static constexpr int CPT = C > 32 ? 16 : 8;                 // channels per epilogue thread
-    static constexpr int GE = C / CPT;                           // epilogue warp groups per 128-row tile
+    static constexpr int CPT = C >= 16 ? 16 : 8;                // channels per epilogue thread
+    static constexpr int GE = C / CPT;                           // sets of 4 epilogue warps per 128-row tile
+    // NG epilogue groups work on different resblocks at the same time: group 0 owns the k = 11 resblock, group 1 the other
+    // two (6 and 12 jobs per tile; one group for all 18 made the epilogue, not the tensor core, the limiter of a tile)
+    static constexpr int NG = NCH == 3 ? 2 : 1;
     // byte offsets; with NCH = 1 the single chain is sized for the largest kernel (local index 0 = k 11)
     __host__ __device__ static constexpr int a1(int c) { return c == 0 ? 0 : a1(c - 1) + 2 * G * um_R1(c - 1, TT) * 16; }
     __host__ __device__ static constexpr int a2(int c) { return c == 0 ? a1(NCH) : a2(c - 1) + 2 * G * um_R2(c - 1, TT) * 16; }
@@ -621,8 +624,11 @@ struct UmLayout {
     // of width 2 N: main and aux accumulator) + a_lo w_hi (width N): the activation operand, whose fetch from shared
     // memory bounds these narrow MMAs, is read twice per k16 step instead of three times; the epilogue adds main + aux.
     static constexpr int tile_cols = 4 * N * NCH;
-    static constexpr int tmem_cols = tile_cols * MT <= 128 ? 128 : tile_cols * MT <= 256 ? 256 : 512;
-    static constexpr int threads = 128 + 128 * GE * MT;
+    static constexpr int scratch_col = tile_cols * MT;                     // N columns per row tile: group 0's output sum for group 1
+    static constexpr int cols_used = scratch_col + (NG == 2 ? N * MT : 0);
+    static constexpr int tmem_cols = cols_used <= 128 ? 128 : cols_used <= 256 ? 256 : 512;
+    static_assert(cols_used <= 512, "tensor memory");
+    static constexpr int threads = 128 + NG * 128 * GE * MT;
 };
 
 // The transposed convolution that opens a stage runs as its own kernel (upsample_kernel) and leaves x0 [B, n_out, C] in
@@ -822,7 +828,7 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
     constexpr int HALO = 12 * (11 - 1);
     constexpr int UM_THREADS = L::threads;             // warps 0-3: MMA issue, weight stream, 2 idle; then GE MT epilogue groups of 4 warps
     extern __shared__ __align__(1024) unsigned char um_smem[];
-    __shared__ __align__(8) uint64_t a_ready[3], d_ready[3], w_full[UM_WSLOTS], w_empty[UM_WSLOTS], x_full, x_empty;
+    __shared__ __align__(8) uint64_t a_ready[3], d_ready[3], w_full[UM_WSLOTS], w_empty[UM_WSLOTS], x_full, x_empty, o_ready, o_free;
     __shared__ uint32_t tmem_slot;
     unsigned char* sm = um_smem;
     const uint32_t sm_a = um_smem_u32(um_smem);
@@ -842,7 +848,7 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
     for (int i = tid; i < L::wring / 16; i += UM_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&a_ready[i])), "r"(4 * GE * MT));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&a_ready[i])), "r"(4 * GE * MT));   // the owning group's warps
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&d_ready[i])), "r"(1));
         }
         for (int i = 0; i < UM_WSLOTS; ++i) {
@@ -850,7 +856,9 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&w_empty[i])), "r"(1));
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&x_full)), "r"(1));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&x_empty)), "r"(4 * GE * MT));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&x_empty)), "r"(L::NG * 4 * GE * MT));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&o_ready)), "r"(4 * GE * MT));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&o_free)), "r"(4 * GE * MT));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
@@ -978,8 +986,10 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
         // =========================== epilogue (thread = time row x CPT channels) ===========================
         // GE MT groups of 4 warps; a group owns CPT channels (S8 operand groups of 8) of the 128 rows of one MMA tile (a
         // warp may only touch the TMEM lane quadrant warp % 4, so each group is one full set of quadrants)
-        constexpr int NE = 128 * GE * MT;
-        const int et = tid - 128, wg = (warp - 4) >> 2, ge = wg % GE, mt = wg / GE, quad = warp & 3;
+        constexpr int NE = 128 * GE * MT, NG = L::NG;  // threads per epilogue group, groups
+        const int grp = (tid - 128) / NE;
+        const int et = (tid - 128) % NE, wg = et >> 7, ge = wg % GE, mt = wg / GE, quad = warp & 3;
+        auto owner = [&](int c) { return NG == 1 ? 0 : (c == 0 ? 0 : 1); };   // epilogue group of local resblock c
         const int g0 = ge * S8;                        // first 8-channel operand group of this thread
         const int pl = quad * 32 + lane;               // TMEM lane = row of the 128-row MMA tile
         const int p = mt * UM_ROWS + pl;               // row of the CTA tile
@@ -987,7 +997,7 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
         (void)pl;
         float* x0 = reinterpret_cast<float*>(sm + L::x0);
         uint32_t d_seen[3] = {0, 0, 0};
-        auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;\n" ::"n"(NE) : "memory"); };
+        auto epi_bar = [&]() { asm volatile("bar.sync %0, %1;\n" ::"r"(1 + grp), "n"(NE) : "memory"); };   // this group only
 
         // writes this thread's CPT channels of its row (already activated) into operand buffer `buf` (rows R, tile starts
         // at row `lead`), and the tail rows additionally into the saved context `ctx` (ctx_rows rows)
@@ -1075,13 +1085,15 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
         // first tile: all resblocks start together.  Later tiles are started resblock by resblock from inside the previous
         // tile's job loop (right after the resblock's last epilogue), so the tensor core never waits for a tile boundary.
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) chain_restore0(c);
+        for (int c = 0; c < NCH; ++c)
+            if (owner(c) == grp) chain_restore0(c);
         um_wait(&x_full, 0);
         epi_bar();                                      // all context rows restored before this tile's tails replace them
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) chain_begin(c);
+        for (int c = 0; c < NCH; ++c)
+            if (owner(c) == grp) chain_begin(c);
         __syncwarp();
-        if (lane == 0) um_arrive(&x_empty);             // the loader may fetch the next tile
+        if (lane == 0) um_arrive(&x_empty);             // the loader may fetch the next tile (once both groups have arrived)
 
         for (int tile = 0; tile < n_tiles; ++tile) {
             const int t0 = t_first + tile * UM_TT;
@@ -1095,6 +1107,7 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                 const UmmaJob jb = a.w.jobs[ji];
                 if (jb.chain < kc0 || jb.chain >= kc0 + NCH) continue;
                 const int kc = jb.chain, c = kc - kc0, l = jb.layer, K = jb.K;
+                if (owner(c) != grp) continue;
                 float v[CPT], pa[CPT], ea[CPT], ieb[CPT];
                 // per-channel constants of this job are fetched while the MMAs are still running
                 if (!jb.conv2) {
@@ -1123,7 +1136,8 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                     if (l < 2) restore(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, c1_off(c, K, l + 1), ctx);
                     else if (start_next) chain_restore0(c);
                     tld(t_lane + c * 4 * N + CPT * ge, v);
-                    if (start_next && c == 0) um_wait(&x_full, (tile + 1) & 1);      // the next x0 tile (loaded during this one)
+                    if (start_next && (c == 0 || (NG == 2 && c == 1))) um_wait(&x_full, (tile + 1) & 1);   // the next x0 tile (loaded
+                                                                                                           // during this one); first use per group
                     epi_bar();
                     if (l < 2) {
 #pragma unroll
@@ -1136,7 +1150,7 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                         if (start_next) {
                             chain_begin(c);
-                            if (c == NCH - 1) {
+                            if (c == NCH - 1 || (NG == 2 && c == 0)) {       // this group's last read of the x0 tile
                                 __syncwarp();
                                 if (lane == 0) um_arrive(&x_empty);
                             }
@@ -1146,15 +1160,39 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                 if (et == 0) UM_TRACE(ji * 4 + 3);
             }
             // ---- channel-last output (warm-up tiles are not written): the mean of the three resblocks, or this one's partial ----
+            const uint32_t t_scr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(L::scratch_col + mt * N + CPT * ge);
+            if (NG == 2 && grp == 0) {
+                // group 0 (k = 11 resblock) finishes first: its sum goes to group 1 through tensor memory (same lane, same columns)
+                if (tile >= 1) um_wait(&o_free, (tile - 1) & 1);
+#pragma unroll
+                for (int s8 = 0; s8 < S8; ++s8) um_st8(t_scr + 8 * s8, osum + 8 * s8);
+                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0) um_arrive(&o_ready);
+                continue;
+            }
+            if (NG == 2) {
+                um_wait(&o_ready, tile & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+                for (int s8 = 0; s8 < S8; ++s8) {
+                    float o0[8];
+                    um_ld8(t_scr + 8 * s8, o0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) osum[8 * s8 + i] += o0[i];
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0) um_arrive(&o_free);
+            }
             const int tg = t0 + p;
             if (t0 >= t_begin && tg < t_end) {
-                const float sc = NCH == 3 ? 1.0f / 3.0f : 1.0f;
                 float* dst = a.out[NCH == 3 ? 0 : kc0] + (size_t)b * a.n_out * C + (size_t)tg * C + CPT * ge;
 #pragma unroll
                 for (int q = 0; q < CPT / 4; ++q)
                     reinterpret_cast<float4*>(dst)[q] = NCH == 3 ? make_float4(osum[4 * q] / 3.0f, osum[4 * q + 1] / 3.0f, osum[4 * q + 2] / 3.0f, osum[4 * q + 3] / 3.0f)
                                                                  : make_float4(osum[4 * q], osum[4 * q + 1], osum[4 * q + 2], osum[4 * q + 3]);
-                (void)sc;
             }
         }
     }
