@@ -723,6 +723,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     } else if (warp == 0) {
         // =========================== MMA warp ===========================
         uint32_t wIt = 0, accIt = 0;
+        uint32_t accUsed = 0, accPar = 0;   // per accumulator slot: used before / parity of the next accEmpty completion
         uint32_t aPar = 0;       // bit c = parity of the next completion of fullA[c] (a register: an indexed array would live in local
                                  // memory, and with ~28 KiB of L1 left next to 228 KiB of shared memory its loads come back from L2)
         bool dead = false;
@@ -734,10 +735,23 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                 for (int j = 0; j < pl.n && !dead; ++j) {
                     const uint32_t e = ctl.ent[pl.e_off + j];
                     const int bn = ctl.ops[e >> 8].bn;
-                    const int slot = accIt % ACC_SLOTS, round = accIt / ACC_SLOTS;
-                    if (round >= 1 && !mbar_wait<false>(&bars.accEmpty[slot], (round - 1) & 1, abort_flag, 21)) { dead = true; break; }
+                    // A CTA with a single tile in this phase (the regular, latency-bound phases) has tensor memory to spare: it
+                    // issues a_hi x [w_hi | w_lo] as ONE MMA of width 2 bn into [main | aux] (the weight image already stores
+                    // the lo rows right behind the hi rows) plus a_lo x w_hi, i.e. two activation fetches per k16 step instead
+                    // of three, and takes two adjacent accumulator slots for it.  The epilogue adds main + aux.
+                    const bool stacked = pl.n == 1 && ctl.ops[e >> 8].kind != KIND_GRU;
+                    if (stacked && (accIt & 1)) ++accIt;
+                    const int slot = accIt % ACC_SLOTS;
+                    accIt += stacked ? 2 : 1;
+                    for (int q = 0; q < (stacked ? 2 : 1) && !dead; ++q) {
+                        const uint32_t bit = 1u << (slot + q);
+                        if ((accUsed & bit) && !mbar_wait<false>(&bars.accEmpty[slot + q], (accPar >> (slot + q)) & 1u, abort_flag, 21)) dead = true;
+                        if (accUsed & bit) accPar ^= bit;
+                        accUsed |= bit;
+                    }
+                    if (dead) break;
                     tc_fence_after();
-                    const uint32_t idesc = make_idesc(TILE_M, bn);
+                    const uint32_t idesc = make_idesc(TILE_M, bn), idesc2 = make_idesc(TILE_M, 2 * bn);
                     const uint32_t d_tmem = tmem + slot * ACC_COLS;
                     // The tensor pipe runs dry whenever this warp is not issuing (an MMA issues in ~55 clk and executes in ~72), so
                     // the chunks that have already landed are found with one batch of polls instead of one blocking wait each.
@@ -766,11 +780,19 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
                             const uint64_t dwh = descW + (uint64_t)((ws * W_SLOT_BYTES) >> 4);
                             const uint64_t dwl = dwh + (uint64_t)((bn * 128) >> 4);
+                            if (stacked) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {   // small terms first
-                                umma(d_tmem, dal + 2 * ks, dwh + 2 * ks, idesc, (c | ks) != 0 ? 1u : 0u);
-                                umma(d_tmem, dah + 2 * ks, dwl + 2 * ks, idesc, 1u);
-                                umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc, 1u);
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc2, (c | ks) != 0 ? 1u : 0u);
+                                    umma(d_tmem, dal + 2 * ks, dwh + 2 * ks, idesc, 1u);
+                                }
+                            } else {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {   // small terms first
+                                    umma(d_tmem, dal + 2 * ks, dwh + 2 * ks, idesc, (c | ks) != 0 ? 1u : 0u);
+                                    umma(d_tmem, dah + 2 * ks, dwl + 2 * ks, idesc, 1u);
+                                    umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc, 1u);
+                                }
                             }
                             umma_commit(&bars.emptyW[ws]);
                             if (c == nck - 1) umma_commit(&bars.accFull[slot]);
@@ -778,7 +800,6 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         __syncwarp();
                     }
                     if (dead) break;
-                    ++accIt;
                 }
                 if (pl.n > 0 && !dead) {
                     if (elect_one()) umma_commit(&bars.aFree);
@@ -799,7 +820,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
         const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
         const uint32_t stg_send = smem_base + SMEM_STG;
         const unsigned char* stg_recv = smem_gen + SMEM_STG;
-        uint32_t accIt = 0, sIt = 0;
+        uint32_t accIt = 0, sIt = 0, fullPar = 0;      // fullPar: per slot, parity of the next accFull completion
         bool dead = false;
         for (int t = 0; t < T && !dead; ++t) {
             for (int ph = 0; ph < n_phases && !dead; ++ph) {
@@ -808,15 +829,25 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     const uint32_t e = ctl.ent[pl.e_off + j];
                     const Op& op = ctl.ops[e >> 8];
                     const int nt = (int)(e & 0xFF);
-                    const int slot = accIt % ACC_SLOTS, round = accIt / ACC_SLOTS;
-                    ++accIt;
+                    const bool stacked = pl.n == 1 && op.kind != KIND_GRU;   // same rule as in the MMA warp: [main | aux] in two adjacent slots
+                    if (stacked && (accIt & 1)) ++accIt;
+                    const int slot = accIt % ACC_SLOTS;
+                    accIt += stacked ? 2 : 1;
+                    const uint32_t full_parity = (fullPar >> slot) & 1u;
+                    fullPar ^= 1u << slot;
                     const uint32_t taddr = t_lane + slot * ACC_COLS;
+                    auto release_acc = [&]() {              // this warp has drained the accumulator
+                        if (lane == 0) {
+                            mbar_arrive(&bars.accEmpty[slot]);
+                            if (stacked) mbar_arrive(&bars.accEmpty[slot + 1]);
+                        }
+                    };
                     if (op.kind == KIND_GRU) {
                         // ---- 48-wide tile: thread = row, 12 columns = r, z, n of 4 hidden units ----
                         const int col0 = nt * 48 + 12 * rank, u0 = nt * 16 + 4 * rank;
                         Prefetch pf;
                         if (hf == 0) prefetch_epilogue(op, fr, t, m, col0, u0, pf);
-                        if (!mbar_wait<false>(&bars.accFull[slot], round & 1, abort_flag, 31)) { dead = true; break; }
+                        if (!mbar_wait<false>(&bars.accFull[slot], full_parity, abort_flag, 31)) { dead = true; break; }
                         tc_fence_after();
                         const int sr = sIt;
                         ++sIt;
@@ -829,11 +860,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             if (tid == 128) mbar_expect_tx(&bars.stgFull, (uint32_t)((CLUSTER - 1) * TILE_M * 12 * 4));
                             exchange<12>(acc, rank, row, stg_send, smem_u32(&bars.stgFull), own);
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
+                            release_acc();
                             if (!mbar_wait<false>(&bars.stgFull, sr & 1, abort_flag, 33)) { dead = true; break; }
                             reduce_parts<12>(own, rank, row, stg_recv, v);
                         } else {
-                            if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
+                            release_acc();
                             if (sr >= 1 && !mbar_wait<false>(&bars.stgEmpty, (sr - 1) & 1, abort_flag, 32)) { dead = true; break; }
                             if (!mbar_wait<false>(&bars.stgFull, sr & 1, abort_flag, 33)) { dead = true; break; }
                         }
@@ -850,7 +881,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     const int col0 = pl.split ? nt * 64 + 16 * rank + 8 * hf : nt * 16 + 8 * hf;
                     Prefetch8 pf;
                     prefetch8(op, fr, t, m, col0, pf);
-                    if (!mbar_wait<false>(&bars.accFull[slot], round & 1, abort_flag, 31)) { dead = true; break; }
+                    if (!mbar_wait<false>(&bars.accFull[slot], full_parity, abort_flag, 31)) { dead = true; break; }
                     if (tid == 128 && j == 0) BVC_TRACE(8);
                     if (tid == 128 && j == pl.n - 1) BVC_TRACE(9);
                     tc_fence_after();
@@ -862,6 +893,17 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
 #pragma unroll
                         for (int p = 0; p < CLUSTER; ++p) tmem_ld8(taddr + 16 * p + 8 * hf, acc + 8 * p);
                         tmem_ld_wait();
+                        if (stacked) {
+#pragma unroll
+                            for (int p = 0; p < CLUSTER; p += 2) {      // 16 aux columns at a time keeps the register count down
+                                float aux[16];
+                                tmem_ld8(taddr + 64 + 16 * p + 8 * hf, aux);
+                                tmem_ld8(taddr + 64 + 16 * (p + 1) + 8 * hf, aux + 8);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) acc[8 * p + i] += aux[i];
+                            }
+                        }
                         tc_fence_before();
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(10);
                         // my staging slot at every peer is free once all peers have read the previous tile
@@ -871,7 +913,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         exchange8(acc, rank, hf, row, stg_send, smem_u32(&bars.stgFull), own);
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(0);
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
+                        release_acc();
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(11);
                         if (!mbar_wait<false>(&bars.stgFull, sr & 1, abort_flag, 33)) { dead = true; break; }
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(14);
@@ -886,10 +928,17 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(1);
                     } else {
                         tmem_ld8(taddr + 8 * hf, v);
+                        if (stacked) {
+                            float aux[8];
+                            tmem_ld8(taddr + op.bn + 8 * hf, aux);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] += aux[i];
+                        }
                         tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars.accEmpty[slot]);
+                        release_acc();
                     }
                     finalize8(op, fr, t, m, row, m_tile, col0, v, pf);
                 }
