@@ -201,17 +201,6 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
@@ -237,25 +226,6 @@ __device__ __forceinline__ unsigned long long global_ns() {
         if (trace && t < trace_frames) trace[(((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS + (ev)] = global_ns(); \
     } while (0)
 
-// 16 consecutive values of activation row `row` (columns col0 .. col0+15, col0 % 16 == 0) -> image of the
-// consumer layer: two 16-byte pieces of the hi part and of the lo part
-__device__ __forceinline__ void store_img16(unsigned char* img, int m_tile, int kchunks, int row, int col0, const float* v,
-                                            bool zero_lo) {
-    unsigned char* base = img + ((size_t)m_tile * kchunks + (col0 >> 6)) * ACT_CHUNK_BYTES + row * 128;
-    const int ch = (col0 & 63) >> 3;
-    uint4 h0, l0, h1, l1;
-    split_pair(v[0], v[1], h0.x, l0.x);   split_pair(v[2], v[3], h0.y, l0.y);
-    split_pair(v[4], v[5], h0.z, l0.z);   split_pair(v[6], v[7], h0.w, l0.w);
-    split_pair(v[8], v[9], h1.x, l1.x);   split_pair(v[10], v[11], h1.y, l1.y);
-    split_pair(v[12], v[13], h1.z, l1.z); split_pair(v[14], v[15], h1.w, l1.w);
-    if (zero_lo) { l0 = make_uint4(0, 0, 0, 0); l1 = l0; }
-    const int p0 = (ch ^ (row & 7)) << 4, p1 = ((ch + 1) ^ (row & 7)) << 4;
-    *reinterpret_cast<uint4*>(base + p0) = h0;
-    *reinterpret_cast<uint4*>(base + p1) = h1;
-    *reinterpret_cast<uint4*>(base + ACT_PART_BYTES + p0) = l0;
-    *reinterpret_cast<uint4*>(base + ACT_PART_BYTES + p1) = l1;
-}
-
 // loads that may have been written by another CTA in an earlier phase go through L2 (ld.cg)
 __device__ __forceinline__ void load16_cg(const float* p, float* v) {
 #pragma unroll
@@ -271,11 +241,6 @@ __device__ __forceinline__ void load12_cg(const float* p, float* v) {
         v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
     }
 }
-__device__ __forceinline__ void store16(float* p, const float* v) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-
 // Operands of an epilogue that do not depend on the accumulator; fetched while the MMAs are still running.
 struct Prefetch {
     float a[16];     // LINEAR: bias + addend.  GRU: W_ih_z phi_z + b_ih of the 12 columns
@@ -304,48 +269,6 @@ __device__ __forceinline__ void prefetch_epilogue(const Op& op, const Frame& fr,
         for (int i = 0; i < 16; ++i) pf.a[i] += tmp[i];
     }
     if (op.kind == KIND_BOTTLENECK) pf.budget = fr.bits ? __ldg(fr.bits + (size_t)m * fr.T + t) : fr.bits_scalar;
-}
-
-// Epilogue of 16 output columns (col0 .. col0+15) of row m.  v = A.W^T summed over the whole K.
-__device__ __forceinline__ void finalize16(const Op& op, const Frame& fr, int t, int m, int row, int m_tile, int col0,
-                                           float* v, const Prefetch& pf) {
-    if (m >= fr.M) return;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += pf.a[i];
-    if (op.kind == KIND_BOTTLENECK) {
-        // z = round(sigmoid(logit)), masked to 0.5 beyond the frame's bit budget (bvrnn.py:191-196)
-        float code[16];
-        uint32_t word = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const bool active = !fr.var_bit || (pf.budget > (float)(col0 + i));
-            const bool bit = active && (sigmoidf_(v[i]) > 0.5f);
-            code[i] = active ? (bit ? 1.f : 0.f) : 0.5f;
-            if (bit) word |= 1u << i;
-        }
-        store_img16(op.out_img, m_tile, op.out_kchunks, row, col0, code, true);   // {0, .5, 1} are exact in bf16
-        const size_t o = ((size_t)m * fr.T + t) * fr.Z + col0;
-        store16(fr.codes + o, code);
-        if (fr.logits) store16(fr.logits + o, v);
-        if (fr.packed) reinterpret_cast<unsigned short*>(fr.packed)[((size_t)m * fr.T + t) * 4 + (col0 >> 4)] = (unsigned short)word;
-        return;
-    }
-    if (op.act) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
-    }
-    if (op.kind == KIND_MEL) {
-        if (fr.mel_out) {
-            float* mo = fr.mel_out + ((size_t)m * fr.T + t) * fr.X;
-            if (col0 + 16 <= fr.X) store16(mo + col0, v);
-            else
-                for (int i = 0; i < 16; ++i)
-                    if (col0 + i < fr.X) mo[col0 + i] = v[i];
-        }
-        return;
-    }
-    if (op.out_img && col0 < op.N) store_img16(op.out_img, m_tile, op.out_kchunks, row, col0, v, false);
-    if (op.out_f && col0 < op.N) store16(op.out_f + (size_t)m * op.ldo + col0, v);
 }
 
 // GRU epilogue: 12 columns = [r(4) | z(4) | n(4)] of the hidden units u0 .. u0+3 (PyTorch gate order r,z,n;

@@ -605,7 +605,7 @@ __host__ __device__ constexpr int um_R2(int c, int TT) { return (um_K(c) - 1) + 
 template <int C, int U, int MT, int NCH>
 struct UmLayout {
     static constexpr int TT = UM_ROWS * MT;
-    static constexpr int G = C / 8, N = C < 16 ? 16 : C, CIN = 2 * C;
+    static constexpr int G = C / 8, N = C < 16 ? 16 : C;
     static constexpr int CPT = C >= 16 ? 16 : 8;                // channels per epilogue thread
     static constexpr int GE = C / CPT;                           // sets of 4 epilogue warps per 128-row tile
     // NG epilogue groups work on different resblocks at the same time: group 0 owns the k = 11 resblock, group 1 the other
@@ -715,26 +715,6 @@ __device__ __forceinline__ void um_mma(uint32_t tmem_d, uint64_t da, uint64_t db
 }
 __device__ __forceinline__ void um_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(um_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void um_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void um_st16(uint32_t taddr, const float* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-        : "memory");
 }
 __device__ __forceinline__ void um_ld8(uint32_t taddr, float* v) {
     uint32_t r[8];
