@@ -83,6 +83,17 @@ struct StageArgs {
     int dil[3];
     float* out;               // [B, n_out, C] channel-last
     int TT;
+    // fused tail of the vocoder (last stage, last resblock kernel only): mean with the two partials written by the other
+    // resblock kernels -> SnakeBeta -> conv_post -> tanh -> / inv_scale_div -> wav[:n_wav]  (models.py:228-238)
+    const float* post_p1;     // partials [B, n_out, C] of the other two resblocks, summed in the reference's order
+    const float* post_p2;
+    const float* post_ea;
+    const float* post_ieb;
+    const float* post_w;      // [ci][7]
+    const float* post_bias;
+    float post_inv_scale_div;
+    float* wav;               // [B, n_wav]
+    int n_wav;
 };
 
 __device__ __forceinline__ float load_mean(const StageArgs& a, size_t o) {
@@ -378,13 +389,13 @@ struct StreamLayout {
     static constexpr int CTX2 = K - 1;
     static constexpr int CTXSUM = (K - 1) * 9;     // (K-1)(1+3+5) saved rows for the three dilated convs
     // shared memory in 32-bit words for a tile of TT rows (+16 spare rows so that partial warp tiles stay in bounds)
-    static constexpr size_t words(int TT) {
+    static constexpr size_t words(int TT, bool post = false) {
         return (size_t)(TT + 16) * PF + 2 * (size_t)(CTX1 + TT + 16) * PW + 2 * (size_t)(CTX2 + TT + 16) * PW +
-               2 * (size_t)CTXSUM * PW + 2 * (size_t)3 * CTX2 * PW;
+               2 * (size_t)CTXSUM * PW + 2 * (size_t)3 * CTX2 * PW + (post ? (size_t)(TT + 6) * C : 0);
     }
 };
 
-template <int C, int U, int K, int MT>
+template <int C, int U, int K, int MT, bool POST = false>
 __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
     constexpr int CIN = 2 * C;
     constexpr int HALO = 12 * (K - 1);
@@ -403,6 +414,7 @@ __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
     uint32_t* c1l = c1h + L::CTXSUM * PW;
     uint32_t* c2h = c1l + L::CTXSUM * PW;                                // [3][CTX2] saved contexts of the second convs
     uint32_t* c2l = c2h + 3 * CTX2 * PW;
+    float* pact = reinterpret_cast<float*>(c2l + 3 * CTX2 * PW);        // POST: [6 + TT][C] activated mean, 6 rows of history
     const int NJ = TT / U + 1;                                           // low-rate rows j0-1 .. j0+TT/U-1
     uint32_t* xh = s1h;                                                  // [NJ+16][PWI] stage input tile (aliases s1)
     uint32_t* xl = xh + (NJ + 16) * PWI;
@@ -418,6 +430,8 @@ __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
     const int t_first = max(0, t_begin - ((HALOR + TT - 1) / TT) * TT);  // warm-up tiles (outputs discarded)
 
     for (int i = tid; i < 2 * (L::CTXSUM + 3 * CTX2) * PW; i += kThreads) c1h[i] = 0u;   // causal zero history
+    if (POST)
+        for (int i = tid; i < 6 * C; i += kThreads) pact[i] = 0.f;
     __syncthreads();
 
     const size_t boff = (size_t)b * a.in_bstride;
@@ -554,8 +568,45 @@ __global__ void __launch_bounds__(kThreads) stage_stream_kernel(StageArgs a) {
             c1off += ctx;
         }
 
+        if (POST) {
+            // ---- fused tail: the other two resblocks' partials are complete (their kernels ran before this one) ----
+            constexpr int V = C / 4;
+            const float* p1 = a.post_p1 + (size_t)b * a.n_out * C;
+            const float* p2 = a.post_p2 + (size_t)b * a.n_out * C;
+            for (int i = tid; i < TT * V; i += kThreads) {
+                const int tt = i / V, c4 = i - tt * V;
+                const int tg = t0 + tt;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tg < a.n_out) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(cur + tt * PF + c4 * 4);
+                    const float4 x1 = __ldg(reinterpret_cast<const float4*>(p1 + (size_t)tg * C) + c4);
+                    const float4 x2 = __ldg(reinterpret_cast<const float4*>(p2 + (size_t)tg * C) + c4);
+                    const float4 ea = __ldg(reinterpret_cast<const float4*>(a.post_ea) + c4);
+                    const float4 ieb = __ldg(reinterpret_cast<const float4*>(a.post_ieb) + c4);
+                    v.x = snake(((x0.x + x1.x) + x2.x) / 3.0f, ea.x, ieb.x);
+                    v.y = snake(((x0.y + x1.y) + x2.y) / 3.0f, ea.y, ieb.y);
+                    v.z = snake(((x0.z + x1.z) + x2.z) / 3.0f, ea.z, ieb.z);
+                    v.w = snake(((x0.w + x1.w) + x2.w) / 3.0f, ea.w, ieb.w);
+                }
+                *reinterpret_cast<float4*>(pact + (6 + tt) * C + c4 * 4) = v;
+            }
+            __syncthreads();
+            const float bias = __ldg(a.post_bias);
+            for (int tt = tid; tt < TT; tt += kThreads) {
+                const int tg = t0 + tt;
+                if (t0 < t_begin || tg >= t_end || tg >= a.n_wav) continue;
+                float acc = bias;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) acc = fmaf(__ldg(a.post_w + c * 7 + j), pact[(tt + j) * C + c], acc);
+                a.wav[(size_t)b * a.n_wav + tg] = tanhf(acc) / a.post_inv_scale_div;
+            }
+            __syncthreads();
+            for (int i = tid; i < 6 * C; i += kThreads) pact[i] = pact[TT * C + i];      // history for the next tile
+        }
         // ---- write the tile, channel-last, coalesced (warm-up tiles are not written) ----
-        if (t0 >= t_begin) {
+        if (!POST && t0 >= t_begin) {
             constexpr int V = C / 4;
             for (int i = tid; i < TT * V; i += kThreads) {
                 const int tt = i / V, c4 = i - tt * V;
@@ -1473,29 +1524,40 @@ template <int C> struct StreamTile { static constexpr int TT = 128, MT = 1; };
 template <> struct StreamTile<16> { static constexpr int TT = 256, MT = 2; };
 template <> struct StreamTile<8> { static constexpr int TT = 256, MT = 2; };
 
+template <int C, int U, int K, bool POST>
+int launch_stream(StageArgs a, int B, cudaStream_t stream) {
+    constexpr int HALO = 12 * (K - 1);
+    constexpr int TT = StreamTile<C>::TT, MT = StreamTile<C>::MT;
+    a.TT = TT;
+    const size_t smem = StreamLayout<C, K>::words(TT, POST) * 4;
+    static int ctas_per_sm = 0, sms = 0;
+    if (!ctas_per_sm) {
+        BVC_CUDA(cudaFuncSetAttribute(stage_stream_kernel<C, U, K, MT, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        int dev = 0;
+        BVC_CUDA(cudaGetDevice(&dev));
+        BVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        BVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, stage_stream_kernel<C, U, K, MT, POST>, kThreads, smem));
+        if (ctas_per_sm < 1) { set_error("vocoder stage kernel does not fit on an SM"); ctas_per_sm = 0; return BVC_ERR_DEVICE; }
+    }
+    // time ranges per utterance: whole waves of CTAs (pick_ranges), ranges long enough that the warm-up of a range
+    // (12 (K-1) samples) stays small against its length
+    const int tiles_total = (a.n_out + TT - 1) / TT;
+    const int ranges = pick_ranges(B, tiles_total, (HALO + TT - 1) / TT, sms * ctas_per_sm);
+    dim3 grid(ranges, B);
+    stage_stream_kernel<C, U, K, MT, POST><<<grid, kThreads, smem, stream>>>(a);
+    BVC_CHECK_LAUNCH();
+    return BVC_OK;
+}
+
 template <int C, int U, int K>
 int launch_stage(const StageArgs& a_in, int B, int precision, cudaStream_t stream) {
     constexpr int HALO = 12 * (K - 1);
     StageArgs a = a_in;
     if (precision >= 1) {
-        constexpr int TT = StreamTile<C>::TT, MT = StreamTile<C>::MT;
-        a.TT = TT;
-        const size_t smem = StreamLayout<C, K>::words(TT) * 4;
-        static int ctas_per_sm = 0, sms = 0;
-        if (!ctas_per_sm) {
-            BVC_CUDA(cudaFuncSetAttribute(stage_stream_kernel<C, U, K, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            int dev = 0;
-            BVC_CUDA(cudaGetDevice(&dev));
-            BVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            BVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, stage_stream_kernel<C, U, K, MT>, kThreads, smem));
-            if (ctas_per_sm < 1) { set_error("vocoder stage kernel does not fit on an SM"); ctas_per_sm = 0; return BVC_ERR_DEVICE; }
+        if constexpr (C == 8 && K == 3) {
+            if (a.wav) return launch_stream<C, U, K, true>(a, B, stream);
         }
-        // time ranges per utterance: enough CTAs for ~4 waves (tail effect), but ranges long enough that the
-        // warm-up of a range (12 (K-1) samples) stays small against its length
-        const int tiles_total = (a.n_out + TT - 1) / TT;
-        const int ranges = pick_ranges(B, tiles_total, (HALO + TT - 1) / TT, sms * ctas_per_sm);
-        dim3 grid(ranges, B);
-        stage_stream_kernel<C, U, K, MT><<<grid, kThreads, smem, stream>>>(a);
+        return launch_stream<C, U, K, false>(a, B, stream);
     } else {
         dim3 grid((a.n_out + a.TT - 1) / a.TT, B);
         const int WP = a.TT + HALO + 4;
@@ -1590,6 +1652,8 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
     // shared memory for every instruction (~64 clk measured), so with N = C_out it sustains ~40 C_out MAC/clk: twice the
     // mma.sync kernel at C = 32, on par at 16, behind at 8 where the per-job epilogue latency dominates.  Default: stage 1.
     static const int umma_mask = getenv("BVC_VOC_UMMA") ? atoi(getenv("BVC_VOC_UMMA")) : 0x7;
+    static const bool fuse_post = !(getenv("BVC_VOC_FUSE_POST") && atoi(getenv("BVC_VOC_FUSE_POST")) == 0);
+    bool post_done = false;
     bool single[4] = {false, false, false, false};     // stage i wrote one tensor (the mean) instead of three partials
     // ConvTranspose1d of stage i (reads the previous stage's partials or their mean) -> vb.x0
     auto run_upsample = [&](int i) -> int {
@@ -1729,6 +1793,21 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
             for (int q = 0; q < 6; ++q) { a.ea[q] = bw.act[q].ea; a.ieb[q] = bw.act[q].inv_eb; }
             a.out = vb.part[i][j];
             a.TT = kTT[i];
+            a.wav = nullptr;
+            if (i == 3 && j == 0 && precision >= 1 && !w.antialias_post && fuse_post) {
+                // last launch of the vocoder: the k = 3 resblock kernel of the last stage also does the tail
+                // (mean with the k = 7 and k = 11 partials -> SnakeBeta -> conv_post -> tanh), post_kernel is skipped
+                a.post_p1 = vb.part[3][1];
+                a.post_p2 = vb.part[3][2];
+                a.post_ea = w.act_post.ea;
+                a.post_ieb = w.act_post.inv_eb;
+                a.post_w = w.w_post;
+                a.post_bias = w.b_post;
+                a.post_inv_scale_div = inv_scale_div;
+                a.wav = wav;
+                a.n_wav = length < (int)vb.n[4] ? length : (int)vb.n[4];
+                post_done = a.n_wav > 0;
+            }
             int rc;
             switch (i) {
                 case 0: rc = launch_stage_k<64, 8>(bw.k, a, B, precision, stream); break;
@@ -1739,7 +1818,7 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
             if (rc != BVC_OK) return rc;
         }
     }
-    {
+    if (!post_done) {
         PostArgs p;
         p.n_parts = single[3] ? 1 : 3;
         for (int q = 0; q < 3; ++q) p.in_p[q] = vb.part[3][q];

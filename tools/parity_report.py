@@ -6,6 +6,9 @@ Prints one JSON object per case.  Used for bring-up and for the numbers quoted i
 """
 from __future__ import annotations
 
+import os as _os
+_os.environ.setdefault("BVC_VOC_FUSE_POST", "0")   # keep the last stage's partial tensors: the stage taps are compared below
+
 import argparse
 import json
 import os
