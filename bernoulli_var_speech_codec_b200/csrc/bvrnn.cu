@@ -428,7 +428,13 @@ int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
 int cluster_count(int* out) {
     int dev = 0;
     BVC_CUDA(cudaGetDevice(&dev));
-    return rec::max_clusters(dev, out);
+    int rc = rec::max_clusters(dev, out);
+    if (rc) return rc;
+    // experiment / tuning: BVC_REC_CLUSTERS caps the clusters of the persistent kernel (the time loop is latency-bound: at
+    // B = 256 it hardly slows down on half of the SMs)
+    static const int cap = getenv("BVC_REC_CLUSTERS") ? atoi(getenv("BVC_REC_CLUSTERS")) : 0;
+    if (cap > 0 && cap < *out) *out = cap;
+    return BVC_OK;
 }
 
 }  // namespace
