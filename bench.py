@@ -202,7 +202,7 @@ def main():
     n_gpus = world
 
     from bernoulli_var_speech_codec_b200 import BVRNNCodecModel, SCALING
-    from bernoulli_var_speech_codec_b200.sharding import gather_shards
+    from bernoulli_var_speech_codec_b200.sharding import gather_shards_async
     from bernoulli_var_speech_codec_b200.synth import write_synthetic_checkpoints
     ck_dir = os.environ.get("BVC_CKPT_DIR", "/tmp/bvc_ckpts")
     if rank == 0:
@@ -241,16 +241,25 @@ def main():
         mark("encode")
         if events is not None:
             rec_ms["encode"].append(eng.last_recurrent_ms())
+        # the path's only collective is the final gather of codes and audio: the codes travel while the decoder runs, the
+        # first half of the audio while the vocoder works on the second half (NCCL over NVLink, async, same process group)
+        g_codes = gather_shards_async(codes, B * world) if world > 1 else None
         dmel, _ = eng.decode_mel(codes, None)
         mark("decode_mel")
         if events is not None:
             rec_ms["decode_mel"].append(eng.last_recurrent_ms())
+        if world > 1:
+            half = B // 2
+            wav_a = eng.vocode(dmel[:half].contiguous(), L, SCALING)
+            g_a = gather_shards_async(wav_a, half * world)
+            wav_b = eng.vocode(dmel[half:].contiguous(), L, SCALING)
+            g_b = gather_shards_async(wav_b, (B - half) * world)
+            mark("vocode")
+            all_codes, all_a, all_b = g_codes.result(), g_a.result(), g_b.result()
+            mark("gather")
+            return all_codes, (all_a, all_b)
         wav = eng.vocode(dmel, L, SCALING)
         mark("vocode")
-        if world > 1:   # final gather of codes and audio (the path's only collective)
-            gather_shards(codes, B * world)
-            gather_shards(wav, B * world)
-            mark("gather")
         return codes, wav
 
     def step_e2e():

@@ -24,19 +24,44 @@ def local_shard(x: torch.Tensor, group=None) -> torch.Tensor:
     return x[lo:hi]
 
 
-def gather_shards(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
-    """All ranks receive the concatenation of every rank's shard (dim 0), ragged shards allowed."""
+class _Gather:
+    """A gather in flight (see gather_shards_async): result() orders the current stream after the collective."""
+
+    def __init__(self, work, out, sizes, max_n):
+        self.work, self.out, self.sizes, self.max_n = work, out, sizes, max_n
+
+    def result(self) -> torch.Tensor:
+        if self.work is not None:
+            self.work.wait()
+        if self.sizes is None:
+            return self.out
+        parts = [self.out[r * self.max_n: r * self.max_n + (hi - lo)] for r, (lo, hi) in enumerate(self.sizes)]
+        return torch.cat(parts, 0)
+
+
+def gather_shards_async(local: torch.Tensor, n_total: int, group=None) -> _Gather:
+    """Starts the gather of every rank's shard (dim 0) and returns at once; the collective is ordered after the work
+    already queued on the current stream and runs next to whatever is queued afterwards (e.g. the gather of the codes
+    while the decoder runs, the gather of one half of the audio while the vocoder works on the other half).
+    Equal shards go straight into the output (no padding, no concatenation pass); ragged shards are padded."""
     ws = dist.get_world_size(group)
     if ws == 1:
-        return local
+        return _Gather(None, local, None, 0)
     sizes = [shard_bounds(n_total, ws, r) for r in range(ws)]
     max_n = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros((max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
+    ragged = any(hi - lo != max_n for lo, hi in sizes)
+    src = local.contiguous()
+    if ragged:
+        src = torch.zeros((max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        src[: local.shape[0]] = local
     out = torch.empty((ws * max_n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
-    parts = [out[r * max_n: r * max_n + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
-    return torch.cat(parts, 0)
+    work = dist.all_gather_into_tensor(out, src, group=group, async_op=True)
+    return _Gather(work, out, sizes if ragged else None, max_n)
+
+
+def gather_shards(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All ranks receive the concatenation of every rank's shard (dim 0), ragged shards allowed."""
+    return gather_shards_async(local, n_total, group).result()
 
 
 class ShardedCodec:
