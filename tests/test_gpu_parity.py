@@ -198,6 +198,32 @@ def test_larger_batch_properties(model_var, oracle_var):
     _check_case(model_var, oracle_var, x[:2], 3000)
 
 
+def test_full_size_batch_properties(oracle_var, ckpts, cfg_var):
+    """BASELINE configs[1] size (B=256 x 10 s, 3 kbps) on the default tensor-core path: properties that do not need the
+    oracle at that size (mask layout, value sets, batch-size invariance, forward == decode(encode)) plus oracle parity on
+    two of the utterances."""
+    from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
+    m = BVRNNCodecModel(cfg_var, *ckpts).eval()
+    B, L = 256, 220500
+    x = _noise(B, L, 4321)
+    xd = x.to(m.device)
+    codes = m.encode(xd, 3000)
+    assert codes.shape == (B, L // 256, 64)
+    assert bool((codes[:, :, 35:] == 0.5).all()) and bool(((codes[:, :, :35] == 0.0) | (codes[:, :, :35] == 1.0)).all())
+    frac_ones = codes[:, :, :35].mean().item()
+    assert 0.2 < frac_ones < 0.8                                     # the synthetic encoder is not stuck
+    wav = m.decode(codes, L)
+    assert wav.shape == (B, L) and bool(torch.isfinite(wav).all())
+    # rows are independent: a row coded inside the full batch equals the same row coded in a small batch, bit for bit
+    sub = torch.tensor([0, 1, 127, 128, 255])
+    codes_sub = m.encode(xd[sub].contiguous(), 3000)
+    assert torch.equal(codes_sub, codes[sub.to(codes.device)])
+    wav_sub = m.decode(codes_sub, L)
+    assert _snr_db(wav[sub.to(wav.device)], wav_sub) >= 100.0         # vocoder tiling depends on B: equal to fp32 rounding
+    assert _snr_db(wav[:8], m(xd[:8].contiguous(), 3000)) >= 90.0     # one-recurrence forward
+    _check_case(m, oracle_var, x[126:128], 3000)
+
+
 def _snr_db(ref, test):
     return snr_db(ref.detach().cpu().numpy(), test.detach().cpu().numpy())
 
