@@ -32,6 +32,8 @@ struct bvc_handle {
     int precision = 1;   // 1: split-bf16 tensor-core kernels (default, the measured path); 0: fp32 FFMA kernels
     std::vector<void*> allocs;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // device-to-host copies of the host entry points that overlap later kernels
+    cudaEvent_t copy_ready = nullptr, copy_done = nullptr;
     cudaEvent_t ws_event = nullptr;   // end of the last job that used the workspace (any stream)
     bool ws_event_valid = false;
 };
@@ -337,6 +339,9 @@ int bvc_create(bvc_handle** out, const bvc_config* cfg) {
     cudaSetDevice(cfg->device);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ws_event, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->copy_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->copy_done, cudaEventDisableTiming);
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
         delete h;
@@ -356,6 +361,9 @@ int bvc_destroy(bvc_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->ws.base) cudaFree(h->ws.base);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->copy_ready) cudaEventDestroy(h->copy_ready);
+    if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->ws_event) cudaEventDestroy(h->ws_event);
     if (h->bw.rw.prog_host) cudaFreeHost(h->bw.rw.prog_host);
     cudaSetDevice(prev);
@@ -916,9 +924,28 @@ int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T
     BVC_CUDA(cudaMemcpyAsync(codes, codes_host, ncodes * sizeof(float), cudaMemcpyHostToDevice, s));
     rc = bvrnn_decode(h->bw, h->ws, codes, nullptr, B, T, mel, nullptr, h->precision, s);
     if (rc) return rc;
-    rc = vocoder_forward(h->vw, h->ws, h->vb, mel, B, T, length, inv_scale_div, wav, h->precision, s);
+    // Large batches are synthesised in two halves so that the device-to-host copy of the first half (PCIe, ~2 ms per
+    // 100 MB) runs on the copy stream while the vocoder works on the second half (utterances are independent).
+    const int Ba = (B >= 16 && nwav * sizeof(float) >= ((size_t)32 << 20)) ? B / 2 : B;
+    const size_t mark = h->ws.used;
+    rc = vocoder_forward(h->vw, h->ws, h->vb, mel, Ba, T, length, inv_scale_div, wav, h->precision, s);
     if (rc) return rc;
-    if (nwav) BVC_CUDA(cudaMemcpyAsync(wav_host, wav, nwav * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (Ba < B) {
+        const size_t na = (size_t)Ba * n_out;
+        BVC_CUDA(cudaEventRecord(h->copy_ready, s));
+        BVC_CUDA(cudaStreamWaitEvent(h->copy_stream, h->copy_ready, 0));
+        if (na) BVC_CUDA(cudaMemcpyAsync(wav_host, wav, na * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+        BVC_CUDA(cudaEventRecord(h->copy_done, h->copy_stream));
+        h->ws.used = mark;      // the first half's intermediates are dead in stream order; its output lies outside them
+        rc = vocoder_forward(h->vw, h->ws, h->vb, mel + (size_t)Ba * T * X, B - Ba, T, length, inv_scale_div, wav + na,
+                             h->precision, s);
+        if (rc) return rc;
+        if (nwav - na)
+            BVC_CUDA(cudaMemcpyAsync(wav_host + na, wav + na, (nwav - na) * sizeof(float), cudaMemcpyDeviceToHost, s));
+        BVC_CUDA(cudaStreamWaitEvent(s, h->copy_done, 0));   // the workspace (it holds wav) is released after both copies
+    } else if (nwav) {
+        BVC_CUDA(cudaMemcpyAsync(wav_host, wav, nwav * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
     if ((rc = ws_release(h, s))) return rc;
     BVC_CUDA(cudaStreamSynchronize(s));
     return BVC_OK;
