@@ -56,6 +56,8 @@ SYMBOLS = {
     "bvc_kernel_launches": (C.c_int64, [_P]),
     "bvc_set_precision": (C.c_int, [_P, _I]),
     "bvc_last_recurrent_ms": (C.c_float, [_P]),
+    "bvc_recurrent_ms": (C.c_float, [_P, _I, _I]),
+    "bvc_check": (C.c_int, [_P]),
     "bvc_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
 }
 

@@ -94,7 +94,7 @@ class _Engine:
     def __init__(self, conf: dict, device: torch.device):
         self.lib = _lib.load()
         self.pinned = _PinnedPool(self.lib)
-        if self.lib.bvc_abi_version() != 2:
+        if self.lib.bvc_abi_version() != 3:
             raise RuntimeError("libbvc ABI version mismatch")
         v = conf["vocoder_config"]
         if v.get("activation", "snakebeta") != "snakebeta" or not v.get("snake_logscale", True):
@@ -271,8 +271,16 @@ class _Engine:
         return int(self.lib.bvc_kernel_launches(self.handle))
 
     def last_recurrent_ms(self):
-        """Device time of the persistent recurrent kernel of the last encode / decode_mel call (CUDA events)."""
+        """Device time of the persistent recurrent kernel of the last encode / decode_mel call (CUDA events); waits for it."""
         return float(self.lib.bvc_last_recurrent_ms(self.handle))
+
+    def recurrent_ms(self, kind, age=0):
+        """Device time of the recurrent kernel of the age-th latest call of a kind (0 encode, 1 decode); -1 if not in the ring."""
+        return float(self.lib.bvc_recurrent_ms(self.handle, int(kind), int(age)))
+
+    def check(self):
+        """Waits for the recurrent-kernel launches enqueued so far and raises if one of them aborted (bvc_check)."""
+        _lib.check(self.lib.bvc_check(self.handle), "bvc_check")
 
     def set_precision(self, mode):
         _lib.check(self.lib.bvc_set_precision(self.handle, int(mode)), "set_precision")

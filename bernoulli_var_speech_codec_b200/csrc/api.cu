@@ -16,6 +16,13 @@ static thread_local std::string g_error;
 thread_local int64_t* g_launch_counter = nullptr;
 void set_error(const std::string& msg) { g_error = msg; }
 
+int ws_check(const Workspace& ws, const char* where) {
+    if (!ws.overflow) return BVC_OK;
+    set_error(std::string(where) + ": workspace takes exceed the sized allocation (" + std::to_string(ws.bytes >> 20) +
+              " MiB): sizing formula out of step with the buffers taken");
+    return BVC_ERR_NOMEM;
+}
+
 }  // namespace bvc
 
 using namespace bvc;
@@ -274,6 +281,7 @@ int ensure_workspace(bvc_handle* h, size_t floats) {
         h->ws.bytes = bytes;
     }
     h->ws.used = 0;
+    h->ws.overflow = false;
     return BVC_OK;
 }
 
@@ -365,7 +373,7 @@ int bvc_destroy(bvc_handle* h) {
     if (h->copy_ready) cudaEventDestroy(h->copy_ready);
     if (h->copy_done) cudaEventDestroy(h->copy_done);
     if (h->ws_event) cudaEventDestroy(h->ws_event);
-    if (h->bw.rw.prog_host) cudaFreeHost(h->bw.rw.prog_host);
+    rec_free_slots(h->bw.rw);
     cudaSetDevice(prev);
     delete h;
     return BVC_OK;
@@ -515,14 +523,13 @@ int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
         W(to_vec(m["phi_z.0.weight"]), Hi, Zi, 256, &rw.g_pz0);
         W(to_vec(m["phi_z.2.weight"]), Hi, Hi, 256, &rw.g_pz2);
         W(to_vec(m["phi_z.4.weight"]), Hi, Hi, 256, &rw.g_pz4);
-        void* p1 = nullptr; void* p2 = nullptr; void* p3 = nullptr;
+        void* p1 = nullptr; void* p2 = nullptr;
         ok = ok && cudaMalloc(&p1, rec::SYNC_WORDS * sizeof(unsigned)) == cudaSuccess &&
-             cudaMalloc(&p2, sizeof(rec::Program)) == cudaSuccess && cudaMallocHost(&p3, sizeof(rec::Program)) == cudaSuccess;
+             cudaMalloc(&p2, sizeof(rec::Program)) == cudaSuccess;
         if (p1) h->allocs.push_back(p1);
         if (p2) h->allocs.push_back(p2);
         rw.sync_words = (unsigned*)p1;
         rw.prog_dev = (rec::Program*)p2;
-        rw.prog_host = (rec::Program*)p3;
         rw.ready = ok && (H % 256 == 0) && Z == 64 && X <= 128;
     }
     REQUIRE(ok, BVC_ERR_NOMEM, "device allocation failed while loading BVRNN weights");
@@ -811,14 +818,19 @@ int bvc_encode_mel(bvc_handle* h, const float* mel_dev, const float* bits_dev, f
     if (T == 0) return BVC_OK;
     Guard g(h);
     if (!g.ok) return BVC_ERR_DEVICE;
-    int rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T));
+    int rc = rec_poll_aborts(h->bw.rw, false);      // a finished earlier launch that aborted is reported here
     if (rc) return rc;
+    if (packed_dev && h->bw.Z != 64) {
+        set_error("bvc_encode: packed output needs z_dim == 64 (one uint64 word per frame)");
+        return BVC_ERR_INVALID;
+    }
+    if ((rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T)))) return rc;
     if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
     rc = bvrnn_encode(h->bw, h->ws, mel_dev, bits_dev, bits_scalar, h0_dev, B, T, codes_dev,
                       (unsigned long long*)packed_dev, logits_dev, all_h_dev, h_final_dev, mel_hat_dev, h->precision,
                       (cudaStream_t)stream);
-    if (rc) return rc;
-    return ws_release(h, (cudaStream_t)stream);
+    const int rc2 = ws_release(h, (cudaStream_t)stream);   // also on errors: work may already be enqueued
+    return rc ? rc : rc2;
 }
 
 int bvc_unpack_codes(bvc_handle* h, const uint64_t* packed_dev, const float* bits_dev, float bits_scalar, int32_t B,
@@ -839,13 +851,14 @@ int bvc_decode_mel(bvc_handle* h, const float* codes_dev, const float* h0_dev, i
     if (T == 0) return BVC_OK;
     Guard g(h);
     if (!g.ok) return BVC_ERR_DEVICE;
-    int rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T));
+    int rc = rec_poll_aborts(h->bw.rw, false);
     if (rc) return rc;
+    if ((rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T)))) return rc;
     if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
     rc = bvrnn_decode(h->bw, h->ws, codes_dev, h0_dev, B, T, mel_dev, h_final_dev, h->precision,
                       (cudaStream_t)stream);
-    if (rc) return rc;
-    return ws_release(h, (cudaStream_t)stream);
+    const int rc2 = ws_release(h, (cudaStream_t)stream);
+    return rc ? rc : rc2;
 }
 
 int64_t bvc_vocoder_out_len(const bvc_handle* h, int32_t T) {
@@ -867,8 +880,8 @@ int bvc_vocode(bvc_handle* h, const float* mel_dev, int32_t B, int32_t T, int32_
     if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
     rc = vocoder_forward(h->vw, h->ws, h->vb, mel_dev, B, T, length, inv_scale_div, wav_dev, h->precision,
                          (cudaStream_t)stream);
-    if (rc) return rc;
-    return ws_release(h, (cudaStream_t)stream);
+    const int rc2 = ws_release(h, (cudaStream_t)stream);
+    return rc ? rc : rc2;
 }
 
 int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, float scale, float bits_scalar,
@@ -886,20 +899,25 @@ int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, fl
     float* x_dev = h->ws.take(nx);
     float* mel = h->ws.take(nmel);
     float* codes = h->ws.take(ncodes);
+    if ((rc = ws_check(h->ws, "bvc_encode_host"))) return rc;
     cudaStream_t s = h->stream;
     if ((rc = ws_acquire(h, s))) return rc;
-    BVC_CUDA(cudaMemcpyAsync(x_dev, x_host, nx * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = logmel_forward(h->ft, x_dev, B, L, h->cfg.hop, h->cfg.pad_left, scale, mel, s);
-    if (rc) return rc;
-    if (T > 0) {
-        rc = bvrnn_encode(h->bw, h->ws, mel, nullptr, bits_scalar, nullptr, B, T, codes, nullptr, nullptr, nullptr,
-                          nullptr, nullptr, h->precision, s);
-        if (rc) return rc;
-        BVC_CUDA(cudaMemcpyAsync(codes_host, codes, ncodes * sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
-    if ((rc = ws_release(h, s))) return rc;
+    rc = [&]() -> int {
+        BVC_CUDA(cudaMemcpyAsync(x_dev, x_host, nx * sizeof(float), cudaMemcpyHostToDevice, s));
+        int r = logmel_forward(h->ft, x_dev, B, L, h->cfg.hop, h->cfg.pad_left, scale, mel, s);
+        if (r) return r;
+        if (T > 0) {
+            r = bvrnn_encode(h->bw, h->ws, mel, nullptr, bits_scalar, nullptr, B, T, codes, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, h->precision, s);
+            if (r) return r;
+            BVC_CUDA(cudaMemcpyAsync(codes_host, codes, ncodes * sizeof(float), cudaMemcpyDeviceToHost, s));
+        }
+        return BVC_OK;
+    }();
+    const int rc2 = ws_release(h, s);
+    if (rc || rc2) return rc ? rc : rc2;
     BVC_CUDA(cudaStreamSynchronize(s));
-    return BVC_OK;
+    return rec_poll_aborts(h->bw.rw, true);
 }
 
 int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T, int32_t length, float inv_scale_div,
@@ -919,39 +937,61 @@ int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T
     float* codes = h->ws.take(ncodes);
     float* mel = h->ws.take(nmel);
     float* wav = h->ws.take(nwav);
+    if ((rc = ws_check(h->ws, "bvc_decode_host"))) return rc;
     cudaStream_t s = h->stream;
     if ((rc = ws_acquire(h, s))) return rc;
-    BVC_CUDA(cudaMemcpyAsync(codes, codes_host, ncodes * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = bvrnn_decode(h->bw, h->ws, codes, nullptr, B, T, mel, nullptr, h->precision, s);
-    if (rc) return rc;
-    // Large batches are synthesised in two halves so that the device-to-host copy of the first half (PCIe, ~2 ms per
-    // 100 MB) runs on the copy stream while the vocoder works on the second half (utterances are independent).
-    const int Ba = (B >= 16 && nwav * sizeof(float) >= ((size_t)32 << 20)) ? B / 2 : B;
-    const size_t mark = h->ws.used;
-    rc = vocoder_forward(h->vw, h->ws, h->vb, mel, Ba, T, length, inv_scale_div, wav, h->precision, s);
-    if (rc) return rc;
-    if (Ba < B) {
-        const size_t na = (size_t)Ba * n_out;
-        BVC_CUDA(cudaEventRecord(h->copy_ready, s));
-        BVC_CUDA(cudaStreamWaitEvent(h->copy_stream, h->copy_ready, 0));
-        if (na) BVC_CUDA(cudaMemcpyAsync(wav_host, wav, na * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-        BVC_CUDA(cudaEventRecord(h->copy_done, h->copy_stream));
-        h->ws.used = mark;      // the first half's intermediates are dead in stream order; its output lies outside them
-        rc = vocoder_forward(h->vw, h->ws, h->vb, mel + (size_t)Ba * T * X, B - Ba, T, length, inv_scale_div, wav + na,
-                             h->precision, s);
-        if (rc) return rc;
-        if (nwav - na)
-            BVC_CUDA(cudaMemcpyAsync(wav_host + na, wav + na, (nwav - na) * sizeof(float), cudaMemcpyDeviceToHost, s));
-        BVC_CUDA(cudaStreamWaitEvent(s, h->copy_done, 0));   // the workspace (it holds wav) is released after both copies
-    } else if (nwav) {
-        BVC_CUDA(cudaMemcpyAsync(wav_host, wav, nwav * sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
-    if ((rc = ws_release(h, s))) return rc;
+    rc = [&]() -> int {
+        BVC_CUDA(cudaMemcpyAsync(codes, codes_host, ncodes * sizeof(float), cudaMemcpyHostToDevice, s));
+        int r = bvrnn_decode(h->bw, h->ws, codes, nullptr, B, T, mel, nullptr, h->precision, s);
+        if (r) return r;
+        // Large batches are synthesised in two halves so that the device-to-host copy of the first half (PCIe, ~2 ms per
+        // 100 MB) runs on the copy stream while the vocoder works on the second half (utterances are independent).
+        const int Ba = (B >= 16 && nwav * sizeof(float) >= ((size_t)32 << 20)) ? B / 2 : B;
+        const size_t mark = h->ws.used;
+        r = vocoder_forward(h->vw, h->ws, h->vb, mel, Ba, T, length, inv_scale_div, wav, h->precision, s);
+        if (r) return r;
+        if (Ba < B) {
+            const size_t na = (size_t)Ba * n_out;
+            BVC_CUDA(cudaEventRecord(h->copy_ready, s));
+            BVC_CUDA(cudaStreamWaitEvent(h->copy_stream, h->copy_ready, 0));
+            if (na) BVC_CUDA(cudaMemcpyAsync(wav_host, wav, na * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+            BVC_CUDA(cudaEventRecord(h->copy_done, h->copy_stream));
+            h->ws.used = mark;      // the first half's intermediates are dead in stream order; its output lies outside them
+            r = vocoder_forward(h->vw, h->ws, h->vb, mel + (size_t)Ba * T * X, B - Ba, T, length, inv_scale_div, wav + na,
+                                h->precision, s);
+            if (r) return r;
+            if (nwav - na)
+                BVC_CUDA(cudaMemcpyAsync(wav_host + na, wav + na, (nwav - na) * sizeof(float), cudaMemcpyDeviceToHost, s));
+            BVC_CUDA(cudaStreamWaitEvent(s, h->copy_done, 0));   // the workspace (it holds wav) is released after both copies
+        } else if (nwav) {
+            BVC_CUDA(cudaMemcpyAsync(wav_host, wav, nwav * sizeof(float), cudaMemcpyDeviceToHost, s));
+        }
+        return BVC_OK;
+    }();
+    const int rc2 = ws_release(h, s);
+    if (rc || rc2) return rc ? rc : rc2;
     BVC_CUDA(cudaStreamSynchronize(s));
-    return BVC_OK;
+    return rec_poll_aborts(h->bw.rw, true);
 }
 
-float bvc_last_recurrent_ms(const bvc_handle* h) { return h ? h->bw.rw.last_kernel_ms : 0.f; }
+float bvc_last_recurrent_ms(const bvc_handle* h) {
+    const float ms = bvc_recurrent_ms(const_cast<bvc_handle*>(h), -1, 0);
+    return ms < 0.f ? 0.f : ms;
+}
+
+float bvc_recurrent_ms(bvc_handle* h, int32_t kind, int32_t age) {
+    if (!h) return -1.f;
+    Guard g(h);
+    if (!g.ok) return -1.f;
+    return rec_launch_ms(h->bw.rw, kind, age);
+}
+
+int bvc_check(bvc_handle* h) {
+    REQUIRE(h, BVC_ERR_INVALID, "bvc_check: null handle");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    return rec_poll_aborts(h->bw.rw, true);
+}
 
 int bvc_host_alloc(void** out, size_t bytes) {
     REQUIRE(out && bytes > 0, BVC_ERR_INVALID, "bvc_host_alloc: bad argument");

@@ -167,6 +167,7 @@ static int bvrnn_encode_layers(BvrnnWeights& w, Workspace& ws, const float* mel,
     float* gi = ws.take((size_t)B * 3 * H);
     float* hA = ws.take((size_t)B * H);
     float* hB = ws.take((size_t)B * H);
+    BVC_TRY(ws_check(ws, "BVRNN.encode (layer path)"));
 
     // hoisted: yn -> phi_x(yn) for all frames -> enc.0[:, :H] . phi_x    (bvrnn.py:173,178,189)
     {
@@ -245,6 +246,7 @@ static int bvrnn_decode_layers(BvrnnWeights& w, Workspace& ws, const float* code
     float* gi = ws.take((size_t)B * 3 * H);
     float* hA = ws.take((size_t)B * H);
     float* hB = ws.take((size_t)B * H);
+    BVC_TRY(ws_check(ws, "BVRNN.decode (layer path)"));
 
     // hoisted over all frames: phi_z(z), then [dec.0_z ; W_ih_z] . phi_z + [b_d0 ; b_ih]
     BVC_TRY(run_linear(codes, Z, (int)BT, w.pz0, w.b_pz0, H, PA, H, precision, s));
@@ -373,13 +375,44 @@ unsigned char* take_img(Workspace& ws, int M, int K) {
     return reinterpret_cast<unsigned char*>(ws.take(bytes / sizeof(float)));
 }
 
+std::string abort_message(int flag) {
+    return "recurrent kernel aborted: " +
+           std::string(flag == 1 ? "phase barrier timed out" : "pipeline wait timed out, code " + std::to_string(flag));
+}
+
+// Next staging slot of the launch ring; waits (host) only if the launch that used it 8 launches ago is still running.
+int acquire_slot(RecurrentWeights& rw, int kind, rec::Program** out) {
+    RecurrentWeights::ProgSlot& sl = rw.slots[rw.next_slot];
+    if (!sl.host) {
+        BVC_CUDA(cudaMallocHost((void**)&sl.host, sizeof(rec::Program)));
+        BVC_CUDA(cudaMallocHost((void**)&sl.flag_host, sizeof(int)));
+        BVC_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        BVC_CUDA(cudaEventCreate(&sl.ev_begin));
+        BVC_CUDA(cudaEventCreate(&sl.ev_end));
+    }
+    if (sl.used) {
+        BVC_CUDA(cudaEventSynchronize(sl.done));
+        if (!sl.checked && *sl.flag_host != 0 && !rw.deferred_abort) rw.deferred_abort = *sl.flag_host;
+    }
+    sl.used = false;
+    sl.checked = true;
+    sl.kind = kind;
+    sl.call_id = rw.call_seq;
+    rw.cur_slot = rw.next_slot;
+    rw.next_slot = (rw.next_slot + 1) % RecurrentWeights::PROG_SLOTS;
+    *out = sl.host;
+    return BVC_OK;
+}
+
+// Enqueues program upload, the persistent kernel and the read-back of its abort flag; no host synchronisation.
 int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
+    RecurrentWeights::ProgSlot& sl = w.rw.slots[w.rw.cur_slot];
     if (const char* e = getenv("BVC_REC_DEBUG")) pb.p->debug_flags = atoi(e);
     if (!pb.finish()) {
         set_error("recurrent program does not fit the static limits (m-tiles / entries)");
         return BVC_ERR_INVALID;
     }
-    // bring-up: BVC_REC_TRACE=<file> dumps per-CTA, per-phase %globaltimer stamps of the first frames
+    // bring-up: BVC_REC_TRACE=<file> dumps per-CTA, per-phase %globaltimer stamps of the first frames (synchronous)
     const char* trace_path = getenv("BVC_REC_TRACE");
     const int trace_frames = 6, n_ctas = pb.n_clusters * rec::CLUSTER;
     const size_t trace_n = (size_t)n_ctas * trace_frames * rec::MAX_PHASES * rec::TRACE_EVENTS;
@@ -390,19 +423,18 @@ int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
         pb.p->trace = trace_dev;
         pb.p->trace_frames = trace_frames;
     }
-    BVC_CUDA(cudaMemcpyAsync(w.rw.prog_dev, w.rw.prog_host, sizeof(rec::Program), cudaMemcpyHostToDevice, s));
-    if (!w.rw.ev_begin) {
-        BVC_CUDA(cudaEventCreate(&w.rw.ev_begin));
-        BVC_CUDA(cudaEventCreate(&w.rw.ev_end));
-    }
-    BVC_CUDA(cudaEventRecord(w.rw.ev_begin, s));
+    BVC_CUDA(cudaMemcpyAsync(w.rw.prog_dev, sl.host, sizeof(rec::Program), cudaMemcpyHostToDevice, s));
+    BVC_CUDA(cudaEventRecord(sl.ev_begin, s));
     int rc = rec::launch(w.rw.prog_dev, pb.n_clusters, w.rw.sync_words, s);
     if (rc) return rc;
-    BVC_CUDA(cudaEventRecord(w.rw.ev_end, s));
-    // prog_host is overwritten by the next call, and a failed kernel must be reported by this one
-    BVC_CUDA(cudaStreamSynchronize(s));
-    BVC_CUDA(cudaEventElapsedTime(&w.rw.last_kernel_ms, w.rw.ev_begin, w.rw.ev_end));
+    BVC_CUDA(cudaEventRecord(sl.ev_end, s));
+    *sl.flag_host = 0;
+    BVC_CUDA(cudaMemcpyAsync(sl.flag_host, w.rw.sync_words, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BVC_CUDA(cudaEventRecord(sl.done, s));
+    sl.used = true;
+    sl.checked = false;
     if (trace_dev) {
+        BVC_CUDA(cudaStreamSynchronize(s));
         std::vector<unsigned long long> hbuf(trace_n);
         BVC_CUDA(cudaMemcpy(hbuf.data(), trace_dev, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         cudaFree(trace_dev);
@@ -415,13 +447,6 @@ int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
             fclose(f);
         }
     }
-    int flag = 0;
-    BVC_CUDA(cudaMemcpy(&flag, w.rw.sync_words, sizeof(flag), cudaMemcpyDeviceToHost));
-    if (flag != 0) {
-        set_error("recurrent kernel aborted: " +
-                  std::string(flag == 1 ? "phase barrier timed out" : "pipeline wait timed out, code " + std::to_string(flag)));
-        return BVC_ERR_DEVICE;
-    }
     return BVC_OK;
 }
 
@@ -432,12 +457,71 @@ int cluster_count(int* out) {
     if (rc) return rc;
     // experiment / tuning: BVC_REC_CLUSTERS caps the clusters of the persistent kernel (the time loop is latency-bound: at
     // B = 256 it hardly slows down on half of the SMs)
-    static const int cap = getenv("BVC_REC_CLUSTERS") ? atoi(getenv("BVC_REC_CLUSTERS")) : 0;
+    const char* cap_env = getenv("BVC_REC_CLUSTERS");      // read per call: the chunked-batch test flips it at run time
+    const int cap = cap_env ? atoi(cap_env) : 0;
     if (cap > 0 && cap < *out) *out = cap;
     return BVC_OK;
 }
 
 }  // namespace
+
+// ---- launch ring services ----
+int rec_poll_aborts(RecurrentWeights& rw, bool wait) {
+    for (int i = 0; i < RecurrentWeights::PROG_SLOTS; ++i) {
+        RecurrentWeights::ProgSlot& sl = rw.slots[i];
+        if (!sl.used || sl.checked) continue;
+        if (wait) BVC_CUDA(cudaEventSynchronize(sl.done));
+        else {
+            const cudaError_t q = cudaEventQuery(sl.done);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) { set_error(std::string("recurrent kernel: ") + cudaGetErrorString(q)); return BVC_ERR_DEVICE; }
+        }
+        sl.checked = true;
+        if (*sl.flag_host != 0 && !rw.deferred_abort) rw.deferred_abort = *sl.flag_host;
+    }
+    if (rw.deferred_abort) {
+        set_error(abort_message(rw.deferred_abort) + " (reported by the first call after the failed launch)");
+        rw.deferred_abort = 0;
+        return BVC_ERR_DEVICE;
+    }
+    return BVC_OK;
+}
+
+float rec_launch_ms(RecurrentWeights& rw, int kind, int age) {
+    // distinct call ids of this kind still in the ring, newest first
+    long long ids[RecurrentWeights::PROG_SLOTS];
+    int n = 0;
+    for (int i = 0; i < RecurrentWeights::PROG_SLOTS; ++i) {
+        const RecurrentWeights::ProgSlot& sl = rw.slots[i];
+        if (!sl.used || (kind >= 0 && sl.kind != kind)) continue;
+        bool seen = false;
+        for (int j = 0; j < n; ++j) seen = seen || ids[j] == sl.call_id;
+        if (!seen) ids[n++] = sl.call_id;
+    }
+    std::sort(ids, ids + n, [](long long a, long long b) { return a > b; });
+    if (age < 0 || age >= n) return -1.f;
+    float total = 0.f;
+    for (int i = 0; i < RecurrentWeights::PROG_SLOTS; ++i) {
+        const RecurrentWeights::ProgSlot& sl = rw.slots[i];
+        if (!sl.used || sl.call_id != ids[age] || (kind >= 0 && sl.kind != kind)) continue;
+        float ms = 0.f;
+        if (cudaEventSynchronize(sl.ev_end) == cudaSuccess && cudaEventElapsedTime(&ms, sl.ev_begin, sl.ev_end) == cudaSuccess)
+            total += ms;
+    }
+    return total;
+}
+
+void rec_free_slots(RecurrentWeights& rw) {
+    for (int i = 0; i < RecurrentWeights::PROG_SLOTS; ++i) {
+        RecurrentWeights::ProgSlot& sl = rw.slots[i];
+        if (sl.host) cudaFreeHost(sl.host);
+        if (sl.flag_host) cudaFreeHost(sl.flag_host);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.ev_begin) cudaEventDestroy(sl.ev_begin);
+        if (sl.ev_end) cudaEventDestroy(sl.ev_end);
+        sl = RecurrentWeights::ProgSlot();
+    }
+}
 
 // rows per persistent-kernel call: every m-tile needs a cluster, and the entry table is finite
 static int persistent_max_rows(int n_clusters) {
@@ -473,6 +557,7 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     unsigned char *pzI = take_img(ws, B, H), *d1I = take_img(ws, B, H), *d2I = take_img(ws, B, H);
     unsigned char *d3I = take_img(ws, B, H), *x1I = take_img(ws, B, H), *x2I = take_img(ws, B, H);
     unsigned char* pxI = take_img(ws, B, H);
+    BVC_TRY(ws_check(ws, "BVRNN.encode"));
 
     // hoisted over all frames (tcgen05 GEMMs, gemm_umma.cu): yn = (y - mean) / std -> phi_x -> enc.0[:, :H] . phi_x
     BVC_TRY(to_image(mel, (int)BT, X, w.mean, w.std, ynI, 2, s));
@@ -482,7 +567,8 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     BVC_TRY(linear_umma(PAi, (int)BT, rw.g_e0x, nullptr, 0, E0x, H, nullptr, s));
     BVC_TRY(rec::init_state(h0, hf, hI, B, H, s));
 
-    rec::Program* p = rw.prog_host;
+    rec::Program* p = nullptr;
+    BVC_TRY(acquire_slot(rw, 0, &p));
     memset(p, 0, sizeof(rec::Program));
     rec::Frame& fr = p->frame;
     fr.M = B; fr.T = T; fr.X = X; fr.Z = Z; fr.H = H; fr.var_bit = w.var_bit;
@@ -573,6 +659,7 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     unsigned char *hI = take_img(ws, B, H), *d1I = take_img(ws, B, H), *d2I = take_img(ws, B, H);
     unsigned char *d3I = take_img(ws, B, H), *x1I = take_img(ws, B, H), *x2I = take_img(ws, B, H);
     unsigned char* pxI = take_img(ws, B, H);
+    BVC_TRY(ws_check(ws, "BVRNN.decode"));
 
     // hoisted over all frames (tcgen05 GEMMs): phi_z(z), then [dec.0_z ; W_ih_z (gate-interleaved)] . phi_z + [b_d0 ; b_ih]
     BVC_TRY(to_image(codes, (int)BT, Z, nullptr, nullptr, zI_all, Z / rec::CHUNK_K, s));
@@ -582,7 +669,8 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     BVC_TRY(linear_umma(PAi, (int)BT, rw.g_zcat, rw.b_zcat_q, 0, DZ, 4 * H, nullptr, s));
     BVC_TRY(rec::init_state(h0, hf, hI, B, H, s));
 
-    rec::Program* p = rw.prog_host;
+    rec::Program* p = nullptr;
+    BVC_TRY(acquire_slot(rw, 1, &p));
     memset(p, 0, sizeof(rec::Program));
     rec::Frame& fr = p->frame;
     fr.M = B; fr.T = T; fr.X = X; fr.Z = Z; fr.H = H; fr.var_bit = w.var_bit;
@@ -639,6 +727,7 @@ int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* 
     BVC_TRY(cluster_count(&G));
     const int max_rows = persistent_max_rows(G);
     const size_t mark = ws.used, T_ = (size_t)T;
+    ++w.rw.call_seq;
     for (int b0 = 0; b0 < B; b0 += max_rows) {      // utterances are independent: chunk very large batches
         const int nb = B - b0 < max_rows ? B - b0 : max_rows;
         const size_t r = (size_t)b0;
@@ -659,6 +748,7 @@ int bvrnn_decode(BvrnnWeights& w, Workspace& ws, const float* codes, const float
     BVC_TRY(cluster_count(&G));
     const int max_rows = persistent_max_rows(G);
     const size_t mark = ws.used, T_ = (size_t)T;
+    ++w.rw.call_seq;
     for (int b0 = 0; b0 < B; b0 += max_rows) {
         const int nb = B - b0 < max_rows ? B - b0 : max_rows;
         const size_t r = (size_t)b0;

@@ -109,15 +109,30 @@ struct RecurrentWeights {
     float* b_zcat_q = nullptr;
     unsigned* sync_words = nullptr;  // device: abort flag + one barrier counter per m-tile
     rec::Program* prog_dev = nullptr;
-    rec::Program* prog_host = nullptr;   // pinned staging copy
+    // Launches are asynchronous: a ring of pinned staging slots (program image + the kernel's abort flag read back after
+    // the launch + timing events).  A slot is reused only after its `done` event; the abort flag of a finished launch is
+    // looked at lazily (next entry point on the handle, bvc_check).
+    static constexpr int PROG_SLOTS = 8;
+    struct ProgSlot {
+        rec::Program* host = nullptr;    // pinned
+        int* flag_host = nullptr;        // pinned: sync_words[0] of the launch, copied back in stream order
+        cudaEvent_t done = nullptr, ev_begin = nullptr, ev_end = nullptr;
+        bool used = false, checked = true;
+        int kind = 0;                    // 0 encode, 1 decode
+        long long call_id = 0;
+    } slots[PROG_SLOTS];
+    int next_slot = 0, cur_slot = -1;
+    long long call_seq = 0;
+    int deferred_abort = 0;              // sticky until reported: abort code of an earlier launch
     // parity taps of the last encode call (views into the workspace): dec.0_h . h [B,H], W_hh h + b [B,3H] and
     // W_ih_z phi_z + b [B,3H] of the LAST frame, the latter two with gate-interleaved columns
     const float *tap_dh = nullptr, *tap_gh = nullptr, *tap_giz = nullptr;
     int tap_B = 0;
-    // device time of the last persistent-kernel launch (CUDA events on the launching stream): bench.py's roofline
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    float last_kernel_ms = 0.f;
 };
+// host-side services of the launch ring (bvrnn.cu)
+int rec_poll_aborts(RecurrentWeights& rw, bool wait);                 // BVC_ERR_DEVICE (+ message) if an earlier launch aborted
+float rec_launch_ms(RecurrentWeights& rw, int kind, int age);         // device time of the age-th latest call of `kind` (-1: any); waits for it; -1 if none
+void rec_free_slots(RecurrentWeights& rw);
 
 struct BvrnnWeights {
     int X = 0, H = 0, Z = 0, var_bit = 0;
@@ -140,12 +155,29 @@ struct Workspace {
     float* base = nullptr;
     size_t bytes = 0;
     size_t used = 0;
+    bool overflow = false;     // sticky: a take() went past the allocation (sizing formula out of step with the takes)
+    // Bounds-checked bump allocation.  On overflow the pointer returned still lies inside the allocation (its start),
+    // so nothing is written out of bounds before the entry point sees `overflow` (checked by ws_check() after the
+    // takes of every path) and returns BVC_ERR_NOMEM.
     float* take(size_t n_floats) {
         size_t off = (used + 63) & ~size_t(63);
+        if ((off + n_floats) * sizeof(float) > bytes) {
+            overflow = true;
+            return base;
+        }
         used = off + n_floats;
         return base + off;
     }
 };
+int ws_check(const Workspace& ws, const char* where);
+
+// cudaFuncSetAttribute / occupancy / SM count are per device: one flag (and cached values) per device ordinal.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
 
 size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T);
 int unpack_codes(const unsigned long long* packed, const float* bits, float bits_scalar, int var_bit, size_t n_frames,

@@ -287,11 +287,12 @@ int linear_forward(const float* A, int lda, int M, const LinearWeights& W, const
     if (precision >= 1 && W.w_hi && (K % kTK) == 0) {
         if (M > 512) {
             constexpr int smem = (4 * 128 + 4 * 128) * kTPitch * 4;
-            static bool attr_set = false;
-            if (!attr_set) {
+            static bool attr_set[kMaxDevices] = {};
+            const int dslot = device_slot();
+            if (!attr_set[dslot]) {
                 BVC_CUDA(cudaFuncSetAttribute(linear_bf16x3_kernel<128, 128, 2, 4>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                attr_set = true;
+                attr_set[dslot] = true;
             }
             dim3 grid((N + 127) / 128, (M + 127) / 128);
             linear_bf16x3_kernel<128, 128, 2, 4><<<grid, 256, smem, stream>>>(A, lda, M, W.w_hi, W.w_lo, N, K, ep);

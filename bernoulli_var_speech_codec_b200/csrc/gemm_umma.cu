@@ -290,10 +290,11 @@ int to_image(const float* x, int M, int K_in, const float* mean, const float* sd
 int linear_umma(const unsigned char* a_img, int M, const WImg& w, const float* bias, int act, float* out_f, int ldo,
                 unsigned char* out_img, cudaStream_t stream) {
     if (w.bn != TILE_N || M <= 0) { set_error("linear_umma: weight image must be packed with bn = 256"); return BVC_ERR_INVALID; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};
+    const int dslot = device_slot();
+    if (!attr_set[dslot]) {
         BVC_CUDA(cudaFuncSetAttribute(linear_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
+        attr_set[dslot] = true;
     }
     GemmArgs a;
     a.a_img = a_img; a.w_img = w.img; a.bias = bias; a.out_f = out_f; a.out_img = out_img;

@@ -939,10 +939,11 @@ __global__ void init_state_kernel(const float* __restrict__ h0, float* __restric
 }
 
 int set_attrs() {
-    static bool done = false;
-    if (!done) {
+    static bool done[kMaxDevices] = {};     // the attribute is per device / context
+    const int dslot = device_slot();
+    if (!done[dslot]) {
         BVC_CUDA(cudaFuncSetAttribute(recurrent_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYNAMIC));
-        done = true;
+        done[dslot] = true;
     }
     return BVC_OK;
 }

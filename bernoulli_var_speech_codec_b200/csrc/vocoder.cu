@@ -1238,13 +1238,16 @@ template <int C, int U, int MT, int NCH>
 int launch_stage_umma(const UmmaStageArgs& a, int B, cudaStream_t stream) {
     using L = UmLayout<C, U, MT, NCH>;
     constexpr int UM_TT = L::TT;
-    static int sms = 0;
-    if (!sms) {
+    static int sms_of[kMaxDevices] = {};
+    const int dslot = device_slot();
+    if (!sms_of[dslot]) {
         BVC_CUDA(cudaFuncSetAttribute(stage_umma_kernel<C, U, MT, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
-        int dev = 0;
+        int dev = 0, n = 0;
         BVC_CUDA(cudaGetDevice(&dev));
-        BVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        BVC_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        sms_of[dslot] = n;
     }
+    const int sms = sms_of[dslot];
     // time ranges per utterance: ~4 waves of CTAs, but ranges long enough that their warm-up (120 samples) stays small
     const int ctas_per_range = 3 / NCH;
     const int tiles_total = (a.n_out + UM_TT - 1) / UM_TT;
@@ -1422,10 +1425,11 @@ __global__ void __launch_bounds__(256) conv_cl_kernel(ConvArgs a) {
 template <int C>
 int launch_aa_act(const AaArgs& a, int B, cudaStream_t stream) {
     using L = AaLayout<C>;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[kMaxDevices] = {};
+    const int dslot = device_slot();
+    if (!attr[dslot]) {
         BVC_CUDA(cudaFuncSetAttribute(aa_act_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem));
-        attr = true;
+        attr[dslot] = true;
     }
     aa_act_kernel<C><<<dim3((a.n + L::TT - 1) / L::TT, B), 256, L::smem, stream>>>(a);
     BVC_CHECK_LAUNCH();
@@ -1444,10 +1448,11 @@ template <int C, int K>
 int launch_conv_cl(const ConvArgs& a, int B, cudaStream_t stream) {
     constexpr int TT = 128;
     constexpr size_t smem = 2 * (size_t)((K - 1) * 5 + TT + 16) * RowLayout<C>::PW * 4;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[kMaxDevices] = {};
+    const int dslot = device_slot();
+    if (!attr[dslot]) {
         BVC_CUDA(cudaFuncSetAttribute(conv_cl_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        attr[dslot] = true;
     }
     conv_cl_kernel<C, K><<<dim3((a.n + TT - 1) / TT, B), 256, smem, stream>>>(a);
     BVC_CHECK_LAUNCH();
@@ -1530,15 +1535,19 @@ int launch_stream(StageArgs a, int B, cudaStream_t stream) {
     constexpr int TT = StreamTile<C>::TT, MT = StreamTile<C>::MT;
     a.TT = TT;
     const size_t smem = StreamLayout<C, K>::words(TT, POST) * 4;
-    static int ctas_per_sm = 0, sms = 0;
-    if (!ctas_per_sm) {
+    static int ctas_of[kMaxDevices] = {}, sms_of[kMaxDevices] = {};
+    const int dslot = device_slot();
+    if (!ctas_of[dslot]) {
         BVC_CUDA(cudaFuncSetAttribute(stage_stream_kernel<C, U, K, MT, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        int dev = 0;
+        int dev = 0, n_sm = 0, n_cta = 0;
         BVC_CUDA(cudaGetDevice(&dev));
-        BVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        BVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, stage_stream_kernel<C, U, K, MT, POST>, kThreads, smem));
-        if (ctas_per_sm < 1) { set_error("vocoder stage kernel does not fit on an SM"); ctas_per_sm = 0; return BVC_ERR_DEVICE; }
+        BVC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        BVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n_cta, stage_stream_kernel<C, U, K, MT, POST>, kThreads, smem));
+        if (n_cta < 1) { set_error("vocoder stage kernel does not fit on an SM"); return BVC_ERR_DEVICE; }
+        sms_of[dslot] = n_sm;
+        ctas_of[dslot] = n_cta;
     }
+    const int ctas_per_sm = ctas_of[dslot], sms = sms_of[dslot];
     // time ranges per utterance: whole waves of CTAs (pick_ranges), ranges long enough that the warm-up of a range
     // (12 (K-1) samples) stays small against its length
     const int tiles_total = (a.n_out + TT - 1) / TT;
@@ -1562,10 +1571,11 @@ int launch_stage(const StageArgs& a_in, int B, int precision, cudaStream_t strea
         dim3 grid((a.n_out + a.TT - 1) / a.TT, B);
         const int WP = a.TT + HALO + 4;
         const size_t smem = (size_t)3 * C * WP * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[kMaxDevices] = {};
+        const int dslot = device_slot();
+        if (!attr_set[dslot]) {
             BVC_CUDA(cudaFuncSetAttribute(stage_fp32_kernel<C, U, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-            attr_set = true;
+            attr_set[dslot] = true;
         }
         stage_fp32_kernel<C, U, K><<<grid, kThreads, smem, stream>>>(a);
     }
@@ -1633,6 +1643,7 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
             vb.aa_b = ws.take(x0);
         }
     }
+    if (int rc = ws_check(ws, "vocoder_forward")) return rc;
 
     {
         const size_t total = (size_t)B * (T + 6) * X;

@@ -26,8 +26,21 @@ TAIL = 768                   # samples of a frame's window to the right of its f
 HISTORY_FRAMES = 28          # >= ceil(6719 / 256): the vocoder's receptive field in mel frames
 
 
+def _check_streamable(model):
+    """The chunked paths rely on hop 256 / window 1024 / pad_left 256 and on a strictly causal vocoder."""
+    conf = model.conf
+    if conf["hopsize"] != HOP or conf["winsize"] - conf["mel_pad_left"] != TAIL:
+        raise NotImplementedError("streaming: hopsize / winsize / mel_pad_left differ from the shipped 256 / 1024 / 256")
+    v = conf["vocoder_config"]
+    if any(v.get("layers_antialias", [])) or v.get("antialias_post", False):
+        raise NotImplementedError(
+            "streaming: the anti-aliased Activation1d (symmetric 12-tap FIRs with replicate padding) looks ahead, so "
+            "chunked decoding is not identical to the offline call; use the offline decode for such configs")
+
+
 class StreamingEncoder:
     def __init__(self, model, bitrate):
+        _check_streamable(model)
         self.m, self.eng = model, model._engine
         self.bits = model.bits_per_frame(bitrate)
         self.buf = None          # received samples from global index self.start on
@@ -77,6 +90,7 @@ class StreamingEncoder:
 
 class StreamingDecoder:
     def __init__(self, model):
+        _check_streamable(model)
         self.m, self.eng = model, model._engine
         self.h = None            # BVRNN decoder state [B, H]
         self.mel_hist = None     # last HISTORY_FRAMES decoded mel frames [B, <=28, X]

@@ -18,7 +18,14 @@
  *     owns every input/output buffer; the handle owns packed weights and
  *     workspace.
  *   - `stream` is a cudaStream_t passed as void*.  Device entry points only
- *     enqueue work on it (no host synchronisation) unless stated otherwise.
+ *     enqueue work on it: no host synchronisation, no blocking copy (ABI 3; the
+ *     persistent recurrent kernel's program image goes through a ring of pinned
+ *     staging slots and its abort flag is read back in stream order).  A
+ *     protocol failure inside that kernel (bounded waits, see
+ *     recurrent_cluster.cu) is therefore reported LAZILY: by the next
+ *     bvc_encode* / bvc_decode_mel on the handle that finds the failed launch
+ *     finished, by bvc_check(), or by the *_host entry points (which
+ *     synchronise anyway).  Exceptions are marked "synchronises".
  *   - one handle per device; calls on one handle must be serialised by the
  *     caller.
  *   - there is no CPU path: bvc_create fails with BVC_ERR_DEVICE when the
@@ -35,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BVC_ABI_VERSION 2
+#define BVC_ABI_VERSION 3
 
 typedef enum bvc_status {
     BVC_OK = 0,
@@ -172,6 +179,13 @@ int64_t bvc_kernel_launches(const bvc_handle* h);
 /* Device time in ms (CUDA events on the launching stream) of the persistent recurrent kernel launched by the last
  * bvc_encode / bvc_decode_mel (or their _host variants): the dominant kernel of the path, used for bench.py's roofline. */
 float bvc_last_recurrent_ms(const bvc_handle* h);
+/* ABI 3: the same per kind of call (0 = bvc_encode*, 1 = bvc_decode_mel, -1 = either) and age (0 = the latest such call,
+ * 1 = the one before, ... as long as it is still in the ring of 8 launches), summed over the launches of that call;
+ * -1 if there is no such call.  Both functions wait (host) for that launch to finish; neither is needed for correctness. */
+float bvc_recurrent_ms(bvc_handle* h, int32_t kind, int32_t age);
+/* ABI 3: waits for every recurrent-kernel launch enqueued through this handle and returns BVC_ERR_DEVICE (with
+ * bvc_last_error) if one of them raised its abort flag, BVC_OK otherwise.  Synchronises (only those launches). */
+int bvc_check(bvc_handle* h);
 /* Arithmetic mode of the GEMM/conv inner products: 1 = split-bf16 tensor core (default; the benchmarked path),
  * 0 = fp32 FFMA kernels (slow cross-check path with reference-grade rounding). */
 int bvc_set_precision(bvc_handle* h, int32_t mode);

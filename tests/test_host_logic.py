@@ -28,7 +28,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     for n in names:
         assert n in _lib.SYMBOLS, f"{n} declared in bvc.h but not bound"
         getattr(lib, n)
-    assert lib.bvc_abi_version() == 2
+    assert lib.bvc_abi_version() == 3
 
 
 def test_create_fails_loudly_without_gpu():
