@@ -366,6 +366,7 @@ rec::Op linear_op(const WImg& w, const float* bias, int act, unsigned char* out_
     o.bias = bias; o.act = act;
     o.out_img = out_img; o.out_kchunks = out_kchunks;
     o.kind = rec::KIND_LINEAR;
+    o.stack = 1;      // default for the single-layer phases; the builders clear it for layers that share a phase
     return o;
 }
 
@@ -580,13 +581,13 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     rec::Op o;
     // layers that read h: enc.0_h (critical), dec.0_h and W_hh (consumed later in the frame)
     o = linear_op(rw.e0h, rw.b_e0, 1, e1I, KH);
-    o.addend = E0x; o.ldadd = T * H; o.add_tstride = H;
+    o.addend = E0x; o.ldadd = T * H; o.add_tstride = H; o.stack = 0;
     const int op_e1 = pb.add_op(o);
     o = linear_op(rw.d0h, nullptr, 0, nullptr, 0);
-    o.out_f = dh; o.ldo = H;
+    o.out_f = dh; o.ldo = H; o.stack = 0;
     const int op_dh = pb.add_op(o);
     o = linear_op(rw.whh_q, rw.b_hh_q, 0, nullptr, 0);
-    o.out_f = gh; o.ldo = 3 * H;
+    o.out_f = gh; o.ldo = 3 * H; o.stack = 0;
     const int op_gh = pb.add_op(o);
     const int op_e2 = pb.add_op(linear_op(rw.e2, w.b_e2, 1, e2I, KH));
     o = linear_op(rw.e4, w.b_e4, 0, zI, Z / rec::CHUNK_K);
@@ -597,10 +598,10 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     const int op_pz = pb.add_op(linear_op(rw.pz4, w.b_pz4, 1, pzI, KH));
     // layers that read phi_z: dec.0_z (critical) and W_ih_z (consumed by the GRU)
     o = linear_op(rw.d0z, rw.b_d0, 1, d1I, KH);
-    o.addend = dh; o.ldadd = H;
+    o.addend = dh; o.ldadd = H; o.stack = 0;
     const int op_d1 = pb.add_op(o);
     o = linear_op(rw.ihz_q, rw.b_ih_q, 0, nullptr, 0);
-    o.out_f = giz; o.ldo = 3 * H;
+    o.out_f = giz; o.ldo = 3 * H; o.stack = 0;
     const int op_giz = pb.add_op(o);
     const int op_d2 = pb.add_op(linear_op(rw.d2, w.b_d2, 1, d2I, KH));
     const int op_d3 = pb.add_op(linear_op(rw.d4, w.b_d4, 1, d3I, KH));
@@ -618,7 +619,7 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     const int op_x2 = pb.add_op(linear_op(rw.px2, w.b_px2, 1, x2I, KH));
     const int op_px = pb.add_op(linear_op(rw.px4, w.b_px4, 1, pxI, KH));
     o = linear_op(rw.ihx_q, nullptr, 0, hI, KH);
-    o.kind = rec::KIND_GRU;
+    o.kind = rec::KIND_GRU; o.stack = 0;
     o.addend = giz; o.ldadd = 3 * H;
     const int op_gru = pb.add_op(o);
 
@@ -681,9 +682,10 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     rec::Op o;
     o = linear_op(rw.d0h, nullptr, 1, d1I, KH);
     o.addend = DZ; o.ldadd = T * 4 * H; o.add_tstride = 4 * H;       // includes dec.0 bias
+    o.stack = 0;
     const int op_d1 = pb.add_op(o);
     o = linear_op(rw.whh_q, rw.b_hh_q, 0, nullptr, 0);
-    o.out_f = gh; o.ldo = 3 * H;
+    o.out_f = gh; o.ldo = 3 * H; o.stack = 0;
     const int op_gh = pb.add_op(o);
     const int op_d2 = pb.add_op(linear_op(rw.d2, w.b_d2, 1, d2I, KH));
     const int op_d3 = pb.add_op(linear_op(rw.d4, w.b_d4, 1, d3I, KH));
@@ -694,7 +696,7 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     const int op_x2 = pb.add_op(linear_op(rw.px2, w.b_px2, 1, x2I, KH));
     const int op_px = pb.add_op(linear_op(rw.px4, w.b_px4, 1, pxI, KH));
     o = linear_op(rw.ihx_q, nullptr, 0, hI, KH);
-    o.kind = rec::KIND_GRU;
+    o.kind = rec::KIND_GRU; o.stack = 0;
     o.addend = DZ + H; o.ldadd = T * 4 * H; o.add_tstride = 4 * H;    // W_ih_z phi_z + b_ih, gate-interleaved
     const int op_gru = pb.add_op(o);
 

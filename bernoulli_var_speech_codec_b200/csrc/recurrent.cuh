@@ -45,7 +45,9 @@ struct Op {
     int bn;                        // tile width: 64 (split-K), 48 (GRU, split-K) or 16 (K = 64 layers, no split)
     int kind;
     int act;                       // ELU
-    int pad_;
+    int stack;                     // 1: a_hi x [w_hi | w_lo] as one MMA of width 2 bn into [main | aux] (two adjacent accumulator
+                                   // slots) + a_lo x w_hi; 0: three MMAs into one slot.  A property of the LAYER, not of the
+                                   // schedule, so that a row's arithmetic does not depend on batch size or cluster count.
 };
 
 // All ops of a phase read the same activation matrix A.
@@ -99,7 +101,7 @@ int init_state(const float* h0, float* h, unsigned char* h_img, int M, int H, cu
 int launch(const Program* prog_dev, int n_clusters, unsigned* sync_words /* [0] abort flag, [32 (1 + m)] barrier of m-tile m */,
            cudaStream_t stream);
 constexpr int SYNC_WORDS = 32 * (1 + MAX_MTILES);
-constexpr int TRACE_EVENTS = 16;
+constexpr int TRACE_EVENTS = 24;
 
 }  // namespace rec
 }  // namespace bvc

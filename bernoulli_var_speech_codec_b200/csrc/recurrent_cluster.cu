@@ -221,9 +221,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(v));
     return v;
 }
+// debug flag 64: stamps are the SM's clock64 (exact intervals inside one CTA) instead of %globaltimer (comparable across CTAs,
+// but it ticks in steps of ~0.26 us on this part)
 #define BVC_TRACE(ev)                                                                                             \
     do {                                                                                                          \
-        if (trace && t < trace_frames) trace[(((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS + (ev)] = global_ns(); \
+        if (trace && t < trace_frames)                                                                            \
+            trace[(((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS + (ev)] =            \
+                (dbg_flags & 64) ? (unsigned long long)clock64() : global_ns();                                   \
     } while (0)
 
 // loads that may have been written by another CTA in an earlier phase go through L2 (ld.cg)
@@ -589,8 +593,10 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                 const PhaseLocal& pl = ctl.ph[ph];
                 const int nck = pl.nck;
                 const int nW = pl.n * nck;
+                // experiment (debug flag 128): the CTAs that read the same activation quarter start at different chunks
+                const int rot = ((dbg_flags & 128) && nck == 4 && pl.n > 0) ? (int)(ctl.ent[pl.e_off] & 3) : 0;
                 auto issue_w = [&](int i) {
-                    const int j = i / nck, c = i - j * nck;
+                    const int j = i / nck, c = ((i - j * nck) + rot) & (nck == 4 ? 3 : 0xFF);
                     const uint32_t e = ctl.ent[pl.e_off + j];
                     const Op& op = ctl.ops[e >> 8];
                     const int nt = (int)(e & 0xFF);
@@ -629,8 +635,9 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             // memory; the .global form is a bare FENCE.VIEW.ASYNC.G, the unqualified one adds a MEMBAR.ALL.GPU
                             asm volatile("fence.proxy.async.global;\n" ::: "memory");
                             for (int c = 0; c < nck; ++c) {
+                                const int cs = nck == 4 ? ((c + rot) & 3) : c;
                                 mbar_expect_tx(&bars.fullA[c], ACT_CHUNK_BYTES);
-                                bulk_g2s(smem_base + SMEM_A + c * ACT_CHUNK_BYTES, src + (size_t)c * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES,
+                                bulk_g2s(smem_base + SMEM_A + c * ACT_CHUNK_BYTES, src + (size_t)cs * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES,
                                          &bars.fullA[c]);
                             }
                         }
@@ -662,7 +669,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     // issues a_hi x [w_hi | w_lo] as ONE MMA of width 2 bn into [main | aux] (the weight image already stores
                     // the lo rows right behind the hi rows) plus a_lo x w_hi, i.e. two activation fetches per k16 step instead
                     // of three, and takes two adjacent accumulator slots for it.  The epilogue adds main + aux.
-                    const bool stacked = pl.n == 1 && ctl.ops[e >> 8].kind != KIND_GRU;
+                    const bool stacked = ctl.ops[e >> 8].stack != 0;
                     if (stacked && (accIt & 1)) ++accIt;
                     const int slot = accIt % ACC_SLOTS;
                     accIt += stacked ? 2 : 1;
@@ -731,6 +738,26 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                 }
             }
         }
+    } else if (warp == 2) {
+        // =========================== trace probe (bring-up only) ===========================
+        // An otherwise idle warp watches the activation-chunk barriers and stamps when each chunk has landed, independent
+        // of the MMA warp's own progress (events 16 + c).
+        if (trace && lane == 0) {
+            uint32_t aPar = 0;
+            for (int t = 0; t < T && t < trace_frames; ++t)
+                for (int ph = 0; ph < n_phases; ++ph) {
+                    const PhaseLocal& pl = ctl.ph[ph];
+                    if (pl.n == 0) continue;
+                    for (int c = 0; c < pl.nck && c < 4; ++c) {
+                        const long long t0 = clock64();
+                        while (!mbar_test(&bars.fullA[c], (aPar >> c) & 1u)) {
+                            if (clock64() - t0 > 200000000LL || *(volatile int*)abort_flag) break;
+                        }
+                        BVC_TRACE(16 + c);
+                        aPar ^= 1u << c;
+                    }
+                }
+        }
     } else if (warp >= 4) {
         // =========================== epilogue warps ===========================
         // 8 warps: warp % 4 = TMEM lane quadrant (rows 32 q .. 32 q + 31), hf = (warp - 4) / 4 = column half.  A 64-wide
@@ -752,7 +779,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     const uint32_t e = ctl.ent[pl.e_off + j];
                     const Op& op = ctl.ops[e >> 8];
                     const int nt = (int)(e & 0xFF);
-                    const bool stacked = pl.n == 1 && op.kind != KIND_GRU;   // same rule as in the MMA warp: [main | aux] in two adjacent slots
+                    const bool stacked = op.stack != 0;                      // same rule as in the MMA warp: [main | aux] in two adjacent slots
                     if (stacked && (accIt & 1)) ++accIt;
                     const int slot = accIt % ACC_SLOTS;
                     accIt += stacked ? 2 : 1;

@@ -70,16 +70,16 @@ def logmel(x: torch.Tensor, conf: dict) -> torch.Tensor:
     B, L = x.shape
     if L <= max(pl, pr):
         raise RuntimeError("reflect padding needs L > %d" % max(pl, pr))
-    idx = torch.arange(-pl, L + pr)
+    idx = torch.arange(-pl, L + pr, device=x.device)
     idx = torch.where(idx < 0, -idx, idx)
     idx = torch.where(idx >= L, 2 * (L - 1) - idx, idx)    # reflect, no edge repeat (:80)
     xp = x[:, idx]
     T = 1 + (xp.shape[1] - n_fft) // hop
     frames = xp.unfold(1, n_fft, hop)[:, :T]               # center=False (:84-85)
-    window = torch.hann_window(win, periodic=True, dtype=torch.float32)  # (:70)
+    window = torch.hann_window(win, periodic=True, dtype=torch.float32, device=x.device)  # (:70)
     spec = torch.fft.rfft(frames * window, n=n_fft, dim=-1)
     mag = torch.sqrt(spec.real ** 2 + spec.imag ** 2 + 1e-9)             # (:86-87)
-    basis = torch.from_numpy(slaney_mel(conf["fs"], n_fft, conf["num_mels"], conf["fmin"], conf["fmax"]))
+    basis = torch.from_numpy(slaney_mel(conf["fs"], n_fft, conf["num_mels"], conf["fmin"], conf["fmax"])).to(x.device)
     mel = torch.matmul(mag, basis.t())                                    # (:89)
     return torch.log(torch.clamp(mel, min=1e-5))                          # (:38-39)
 
@@ -117,7 +117,7 @@ def bvrnn_encode(sd, y, bits, h0, var_bit, want_taps=False):
     mean, std = sd["mean_mel"], sd["std_mel"]
     yn = (y - mean) / std                                            # bvrnn.py:173
     phi_x_all = _mlp(sd, "phi_x", (0, 2, 4), yn)                     # :178
-    bit_idx = torch.arange(Z)
+    bit_idx = torch.arange(Z, device=y.device)
     h = h0.clone()
     codes, hs, logits = [], [], []
     for t in range(T):
@@ -264,12 +264,15 @@ class VocoderOracle:
 # facade (reference bvrnn_codec_model.py:19-76)
 # --------------------------------------------------------------------------
 class OracleCodec:
-    def __init__(self, config_path, bvrnn_chkpt_path, vocoder_chkpt_path):
+    def __init__(self, config_path, bvrnn_chkpt_path, vocoder_chkpt_path, device="cpu"):
+        """device: "cpu" (the oracle proper) or a CUDA device -- the same restatement run through PyTorch eager on the GPU
+        (cuBLAS / cuDNN / cuFFT library kernels), which bench.py times as the "PyTorch eager on B200" bar of SURVEY.md 8d."""
         with open(config_path, "rb") as fh:
             self.conf = tomllib.load(fh)
-        self.sd = {k: v.float() for k, v in
+        self.device = torch.device(device)
+        self.sd = {k: v.float().to(self.device) for k, v in
                    torch.load(bvrnn_chkpt_path, map_location="cpu", weights_only=True)["vrnn"].items()}
-        gsd = {k: v.float() for k, v in
+        gsd = {k: v.float().to(self.device) for k, v in
                torch.load(vocoder_chkpt_path, map_location="cpu", weights_only=True)["generator"].items()}
         self.vocoder = VocoderOracle(gsd, self.conf["vocoder_config"])
         self.h_dim = self.conf["h_dim"]
@@ -286,8 +289,8 @@ class OracleCodec:
     def encode(self, x, bitrate, taps=None):
         mel = self.logmel(x)
         B, T, _ = mel.shape
-        bits = torch.full((B, T), self.bits_per_frame(bitrate))
-        h0 = torch.zeros(B, self.h_dim)
+        bits = torch.full((B, T), self.bits_per_frame(bitrate), device=mel.device)
+        h0 = torch.zeros(B, self.h_dim, device=mel.device)
         out = bvrnn_encode(self.sd, mel, bits, h0, self.var_bit, want_taps=taps is not None)
         if taps is not None:
             taps["mel"], taps["all_h"], taps["h_final"], taps["logits"] = mel, out[1], out[2], out[3]
@@ -295,7 +298,7 @@ class OracleCodec:
 
     @torch.no_grad()
     def decode_mel(self, codes, h0=None):
-        h0 = torch.zeros(codes.shape[0], self.h_dim) if h0 is None else h0
+        h0 = torch.zeros(codes.shape[0], self.h_dim, device=codes.device) if h0 is None else h0
         return bvrnn_decode(self.sd, codes.float(), h0)
 
     @torch.no_grad()

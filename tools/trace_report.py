@@ -11,12 +11,30 @@ import sys
 import numpy as np
 
 path = sys.argv[1]
-frame = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+frame = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 3
+CLK = "--clk" in sys.argv     # stamps are clock64 of the CTA's SM (BVC_REC_DEBUG=64): per-CTA intervals from the barrier (event 2)
 hdr = np.fromfile(path, dtype=np.int32, count=4)
 n_cta, n_fr, n_ph, n_ev = [int(v) for v in hdr]
 d = np.fromfile(path, dtype=np.uint64, offset=16).reshape(n_cta, n_fr, n_ph, n_ev).astype(np.float64)
 d[d == 0] = np.nan
 fr = d[:, frame]
+if CLK:
+    ev = [("Aiss", 3), ("A0 mma", 5), ("c0", 16), ("c1", 17), ("c2", 18), ("c3", 19), ("Alast", 6), ("mmaIss", 7), ("acc0", 8),
+          ("accL", 9), ("tmem", 10), ("sent", 11), ("recv", 14), ("sum", 15), ("fin", 12), ("arr", 13)]
+    print("frame %d: %d CTAs; clk after the CTA's own phase-barrier pass (median / max over busy CTAs)" % (frame, n_cta))
+    print("phase busy | " + " ".join("%7s" % n for n, _ in ev))
+    for ph in range(n_ph):
+        if np.all(np.isnan(fr[:, ph, 13])):
+            continue
+        busy = ~np.isnan(fr[:, ph, 8]) & ~np.isnan(fr[:, ph, 2])
+        if not busy.any():
+            continue
+        ref = fr[busy, ph, 2]
+        med = [np.nanmedian(fr[busy, ph, e] - ref) if e < n_ev else np.nan for _, e in ev]
+        mx = [np.nanmax(fr[busy, ph, e] - ref) if e < n_ev else np.nan for _, e in ev]
+        print("%3d  %4d  | " % (ph, int(busy.sum())) + " ".join("%7.0f" % v for v in med))
+        print("       max | " + " ".join("%7.0f" % v for v in mx))
+    sys.exit(0)
 prev_done = np.nanmax(d[:, frame - 1, :, 13]) if frame > 0 else np.nanmin(fr[:, 0, 0])
 order = [2, 3, 4, 5, 6, 7, 8, 9, 10, 0, 11, 14, 15, 1, 12, 13]
 names = ["bar", "Aiss", "Wall", "A0", "Alast", "mma", "acc0", "accL", "tmem", "stores", "sent", "recv", "sum", "freed", "fin", "arr"]
