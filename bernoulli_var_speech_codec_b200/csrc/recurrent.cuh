@@ -101,7 +101,7 @@ int init_state(const float* h0, float* h, unsigned char* h_img, int M, int H, cu
 int launch(const Program* prog_dev, int n_clusters, unsigned* sync_words /* [0] abort flag, [32 (1 + m)] barrier of m-tile m */,
            cudaStream_t stream);
 constexpr int SYNC_WORDS = 32 * (1 + MAX_MTILES);
-constexpr int TRACE_EVENTS = 24;
+constexpr int TRACE_EVENTS = 40;
 
 }  // namespace rec
 }  // namespace bvc

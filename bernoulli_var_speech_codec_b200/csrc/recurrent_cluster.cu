@@ -700,9 +700,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             aPar ^= 1u << c;
                             if (lane == 0 && c == 0) BVC_TRACE(5);
                             if (lane == 0 && c == nck - 1) BVC_TRACE(6);
+                            if (lane == 0 && c < 4) BVC_TRACE(24 + 3 * c);
                         }
                         const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
                         if (!((okW >> c) & 1u) && !mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
+                        if (lane == 0 && j == 0 && c < 4) BVC_TRACE(25 + 3 * c);
                         ++wIt;
                         tc_fence_after();
                         if (elect_one()) {
@@ -728,6 +730,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             if (c == nck - 1) umma_commit(&bars.accFull[slot]);
                         }
                         __syncwarp();
+                        if (lane == 0 && j == 0 && c < 4) BVC_TRACE(26 + 3 * c);
                     }
                     if (dead) break;
                 }
@@ -911,6 +914,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         : "memory");
                     dead = any != 0;
                 }
+                if (tid == 128) BVC_TRACE(36);
                 if (tid == 128) {
                     // The counter is monotonic over all phases, so nobody may arrive for phase p before every CTA
                     // of the domain has arrived for phase p - 1.  A CTA with work in phase p got that from its

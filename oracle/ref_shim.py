@@ -17,7 +17,37 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("BVC_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# On the GPU box /root/reference does not exist; __graft_entry__.build() (run in the build container) copies the handful
+# of reference modules the codec path imports into the git-ignored baseline/_ref/, which travels with the snapshot, so
+# that `bench.py --impl reference` can time the UNMODIFIED reference there.  Never part of the product, never committed.
+BASELINE_REF = os.path.join(_REPO, "baseline", "_ref")
+REFERENCE_ROOT = os.environ.get("BVC_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/bvrnn_codec_model.py") else BASELINE_REF)
+
+REF_FILES = [
+    "bvrnn.py", "bvrnn_codec_model.py", "LICENSE",
+    "third_party/BigVGAN/__init__.py", "third_party/BigVGAN/models.py", "third_party/BigVGAN/activations.py",
+    "third_party/BigVGAN/meldataset.py", "third_party/BigVGAN/env.py", "third_party/BigVGAN/utils.py",
+    "third_party/BigVGAN/LICENSE",
+    "third_party/BigVGAN/alias_free_torch/__init__.py", "third_party/BigVGAN/alias_free_torch/act.py",
+    "third_party/BigVGAN/alias_free_torch/filter.py", "third_party/BigVGAN/alias_free_torch/resample.py",
+]
+
+
+def populate_baseline_ref(src_root: str = "/root/reference") -> bool:
+    """Copies the reference modules of the codec path, byte for byte, into baseline/_ref/ (git-ignored).  Build container only."""
+    import shutil
+    if not os.path.isfile(os.path.join(src_root, "bvrnn_codec_model.py")):
+        return False
+    for rel in REF_FILES:
+        src = os.path.join(src_root, rel)
+        if not os.path.isfile(src):
+            continue
+        dst = os.path.join(BASELINE_REF, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(src, dst)
+    return True
 
 
 def available() -> bool:

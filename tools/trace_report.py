@@ -19,10 +19,12 @@ d = np.fromfile(path, dtype=np.uint64, offset=16).reshape(n_cta, n_fr, n_ph, n_e
 d[d == 0] = np.nan
 fr = d[:, frame]
 if CLK:
-    ev = [("Aiss", 3), ("A0 mma", 5), ("c0", 16), ("c1", 17), ("c2", 18), ("c3", 19), ("Alast", 6), ("mmaIss", 7), ("acc0", 8),
-          ("accL", 9), ("tmem", 10), ("sent", 11), ("recv", 14), ("sum", 15), ("fin", 12), ("arr", 13)]
+    ev = [("Aiss", 3), ("c0", 16), ("c1", 17), ("c2", 18), ("c3", 19),
+          ("A0", 24), ("W0", 25), ("I0", 26), ("A1", 27), ("W1", 28), ("I1", 29), ("A2", 30), ("W2", 31), ("I2", 32),
+          ("A3", 33), ("W3", 34), ("I3", 35), ("mmaIss", 7), ("acc0", 8), ("accL", 9), ("tmem", 10), ("stores", 0), ("sent", 11),
+          ("recv", 14), ("sum", 15), ("freed", 1), ("fin", 12), ("barred", 36), ("arr", 13)]
     print("frame %d: %d CTAs; clk after the CTA's own phase-barrier pass (median / max over busy CTAs)" % (frame, n_cta))
-    print("phase busy | " + " ".join("%7s" % n for n, _ in ev))
+    print("phase busy | " + " ".join("%6s" % n for n, _ in ev))
     for ph in range(n_ph):
         if np.all(np.isnan(fr[:, ph, 13])):
             continue
@@ -32,8 +34,8 @@ if CLK:
         ref = fr[busy, ph, 2]
         med = [np.nanmedian(fr[busy, ph, e] - ref) if e < n_ev else np.nan for _, e in ev]
         mx = [np.nanmax(fr[busy, ph, e] - ref) if e < n_ev else np.nan for _, e in ev]
-        print("%3d  %4d  | " % (ph, int(busy.sum())) + " ".join("%7.0f" % v for v in med))
-        print("       max | " + " ".join("%7.0f" % v for v in mx))
+        print("%3d  %4d  | " % (ph, int(busy.sum())) + " ".join("%6.0f" % v for v in med))
+        print("       max | " + " ".join("%6.0f" % v for v in mx))
     sys.exit(0)
 prev_done = np.nanmax(d[:, frame - 1, :, 13]) if frame > 0 else np.nanmin(fr[:, 0, 0])
 order = [2, 3, 4, 5, 6, 7, 8, 9, 10, 0, 11, 14, 15, 1, 12, 13]
