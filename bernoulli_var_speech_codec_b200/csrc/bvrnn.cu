@@ -408,7 +408,10 @@ int acquire_slot(RecurrentWeights& rw, int kind, rec::Program** out) {
 // Enqueues program upload, the persistent kernel and the read-back of its abort flag; no host synchronisation.
 int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
     RecurrentWeights::ProgSlot& sl = w.rw.slots[w.rw.cur_slot];
-    if (const char* e = getenv("BVC_REC_DEBUG")) pb.p->debug_flags = atoi(e);
+    if (const char* e = getenv("BVC_REC_DEBUG")) {
+        pb.p->debug_flags = atoi(e);
+        pb.p->frame.pad_ = (pb.p->debug_flags & 256) ? 1 : 0;      // timing probe: skip the activation-image stores (wrong results)
+    }
     if (!pb.finish()) {
         set_error("recurrent program does not fit the static limits (m-tiles / entries)");
         return BVC_ERR_INVALID;

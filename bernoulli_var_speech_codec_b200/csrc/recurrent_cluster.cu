@@ -449,7 +449,7 @@ __device__ __forceinline__ void finalize8(const Op& op, const Frame& fr, int t, 
         }
         return;
     }
-    if (op.out_img && col0 < op.N) store_img8(op.out_img, m_tile, op.out_kchunks, row, col0, v, false);
+    if (op.out_img && col0 < op.N && !(fr.pad_ & 1)) store_img8(op.out_img, m_tile, op.out_kchunks, row, col0, v, false);
     if (op.out_f && col0 < op.N) store8(op.out_f + (size_t)m * op.ldo + col0, v);
 }
 // Reduce-scatter of a 128 x 64 partial tile with two threads per row: acc = this thread's 8 columns of each of the four
@@ -658,83 +658,106 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                                  // memory, and with ~28 KiB of L1 left next to 228 KiB of shared memory its loads come back from L2)
         bool dead = false;
         const uint64_t descA = make_desc(smem_base + SMEM_A), descW = make_desc(smem_base + SMEM_W);
+        // One "step" = the MMAs of one 64-wide K chunk of one tile.  The tensor pipe executes in order and its queue is short:
+        // whenever this warp is away from the issue slot for longer than the one or two MMAs still queued (a barrier wait is
+        // 100 - 400 clk), the pipe idles.  Measured in place (profiles/r02_recurrent_trace_clk_*.txt): 860 clk per chunk for
+        // 460 clk of MMA execution.  So the loop is software-pipelined: the waits for the NEXT step (activation chunk, weight
+        // chunk, accumulator slot) are taken in the MIDDLE of the current step's MMAs, while the first half of them executes.
+        struct Step {
+            uint32_t d_tmem, idesc, idesc2, ws, slot, bnw;     // bnw: byte offset (>> 4) of the lo rows inside a weight slot
+            int c;
+            bool stacked, last;
+        };
         for (int t = 0; t < T && !dead; ++t) {
             for (int ph = 0; ph < n_phases && !dead; ++ph) {
                 const PhaseLocal& pl = ctl.ph[ph];
                 const int nck = pl.nck;
-                for (int j = 0; j < pl.n && !dead; ++j) {
-                    const uint32_t e = ctl.ent[pl.e_off + j];
-                    const int bn = ctl.ops[e >> 8].bn;
-                    // A CTA with a single tile in this phase (the regular, latency-bound phases) has tensor memory to spare: it
-                    // issues a_hi x [w_hi | w_lo] as ONE MMA of width 2 bn into [main | aux] (the weight image already stores
-                    // the lo rows right behind the hi rows) plus a_lo x w_hi, i.e. two activation fetches per k16 step instead
-                    // of three, and takes two adjacent accumulator slots for it.  The epilogue adds main + aux.
-                    const bool stacked = ctl.ops[e >> 8].stack != 0;
-                    if (stacked && (accIt & 1)) ++accIt;
-                    const int slot = accIt % ACC_SLOTS;
-                    accIt += stacked ? 2 : 1;
-                    for (int q = 0; q < (stacked ? 2 : 1) && !dead; ++q) {
-                        const uint32_t bit = 1u << (slot + q);
-                        if ((accUsed & bit) && !mbar_wait<false>(&bars.accEmpty[slot + q], (accPar >> (slot + q)) & 1u, abort_flag, 21)) dead = true;
-                        if (accUsed & bit) accPar ^= bit;
-                        accUsed |= bit;
+                const int nsteps = pl.n * nck;
+                if (nsteps == 0) continue;
+                // waits for everything step (j, c) reads; fills `st`
+                auto prepare = [&](int j, int c, Step& st) {
+                    {
+                        const uint32_t e = ctl.ent[pl.e_off + j];
+                        const Op& op = ctl.ops[e >> 8];
+                        st.stacked = op.stack != 0;
+                        st.idesc = make_idesc(TILE_M, op.bn);
+                        st.idesc2 = make_idesc(TILE_M, 2 * op.bn);
+                        st.bnw = (uint32_t)((op.bn * 128) >> 4);
                     }
-                    if (dead) break;
+                    if (c == 0) {
+                        if (st.stacked && (accIt & 1)) ++accIt;
+                        st.slot = accIt % ACC_SLOTS;
+                        accIt += st.stacked ? 2 : 1;
+                        for (int q = 0; q < (st.stacked ? 2 : 1) && !dead; ++q) {
+                            const uint32_t bit = 1u << (st.slot + q);
+                            if ((accUsed & bit) && !mbar_wait<false>(&bars.accEmpty[st.slot + q], (accPar >> (st.slot + q)) & 1u, abort_flag, 21)) dead = true;
+                            if (accUsed & bit) accPar ^= bit;
+                            accUsed |= bit;
+                        }
+                        st.d_tmem = tmem + st.slot * ACC_COLS;
+                    }
+                    st.c = c;
+                    st.last = c == nck - 1;
+                    if (j == 0 && !dead) {
+                        if (!mbar_wait<false>(&bars.fullA[c], (aPar >> c) & 1u, abort_flag, 22)) dead = true;
+                        aPar ^= 1u << c;
+                        if (lane == 0 && c == 0) BVC_TRACE(5);
+                        if (lane == 0 && c == nck - 1) BVC_TRACE(6);
+                    }
+                    st.ws = wIt % W_SLOTS;
+                    if (!dead && !mbar_wait<false>(&bars.fullW[st.ws], (wIt / W_SLOTS) & 1u, abort_flag, 23)) dead = true;
+                    ++wIt;
                     tc_fence_after();
-                    const uint32_t idesc = make_idesc(TILE_M, bn), idesc2 = make_idesc(TILE_M, 2 * bn);
-                    const uint32_t d_tmem = tmem + slot * ACC_COLS;
-                    // The tensor pipe runs dry whenever this warp is not issuing (an MMA issues in ~55 clk and executes in ~72), so
-                    // the chunks that have already landed are found with one batch of polls instead of one blocking wait each.
-                    uint32_t okW = 0, okA = j == 0 ? 0u : 0xFu;
+                };
+                // k16 steps [2 half, 2 half + 1] of a step; the second half also releases the weight slot / completes the accumulator
+                auto issue = [&](const Step& st, int half) {
+                    if (elect_one()) {
+                        const uint64_t dah = descA + (uint64_t)((st.c * ACT_CHUNK_BYTES) >> 4);
+                        const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
+                        const uint64_t dwh = descW + (uint64_t)((st.ws * W_SLOT_BYTES) >> 4);
+                        const uint64_t dwl = dwh + (uint64_t)st.bnw;
+                        if (st.stacked) {
 #pragma unroll
-                    for (int i = 0; i < A_SLOTS; ++i)
-                        if (i < nck) okW |= mbar_test(&bars.fullW[(wIt + i) % W_SLOTS], ((wIt + i) / W_SLOTS) & 1u) << i;
-                    for (int c = 0; c < nck; ++c) {
-                        if (j == 0) {
-                            if (!((okA >> c) & 1u) && !mbar_wait<false>(&bars.fullA[c], (aPar >> c) & 1u, abort_flag, 22)) { dead = true; break; }
-                            if (c == 0) {
-#pragma unroll
-                                for (int i = 1; i < A_SLOTS; ++i)
-                                    if (i < nck) okA |= mbar_test(&bars.fullA[i], (aPar >> i) & 1u) << i;
+                            for (int k2 = 0; k2 < 2; ++k2) {
+                                const int ks = 2 * half + k2;
+                                umma(st.d_tmem, dah + 2 * ks, dwh + 2 * ks, st.idesc2, (st.c | ks) != 0 ? 1u : 0u);
+                                umma(st.d_tmem, dal + 2 * ks, dwh + 2 * ks, st.idesc, 1u);
                             }
-                            aPar ^= 1u << c;
-                            if (lane == 0 && c == 0) BVC_TRACE(5);
-                            if (lane == 0 && c == nck - 1) BVC_TRACE(6);
-                            if (lane == 0 && c < 4) BVC_TRACE(24 + 3 * c);
-                        }
-                        const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
-                        if (!((okW >> c) & 1u) && !mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
-                        if (lane == 0 && j == 0 && c < 4) BVC_TRACE(25 + 3 * c);
-                        ++wIt;
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t dah = descA + (uint64_t)((c * ACT_CHUNK_BYTES) >> 4);
-                            const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
-                            const uint64_t dwh = descW + (uint64_t)((ws * W_SLOT_BYTES) >> 4);
-                            const uint64_t dwl = dwh + (uint64_t)((bn * 128) >> 4);
-                            if (stacked) {
+                        } else {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc2, (c | ks) != 0 ? 1u : 0u);
-                                    umma(d_tmem, dal + 2 * ks, dwh + 2 * ks, idesc, 1u);
-                                }
-                            } else {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {   // small terms first
-                                    umma(d_tmem, dal + 2 * ks, dwh + 2 * ks, idesc, (c | ks) != 0 ? 1u : 0u);
-                                    umma(d_tmem, dah + 2 * ks, dwl + 2 * ks, idesc, 1u);
-                                    umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc, 1u);
-                                }
+                            for (int k2 = 0; k2 < 2; ++k2) {   // small terms first
+                                const int ks = 2 * half + k2;
+                                umma(st.d_tmem, dal + 2 * ks, dwh + 2 * ks, st.idesc, (st.c | ks) != 0 ? 1u : 0u);
+                                umma(st.d_tmem, dah + 2 * ks, dwl + 2 * ks, st.idesc, 1u);
+                                umma(st.d_tmem, dah + 2 * ks, dwh + 2 * ks, st.idesc, 1u);
                             }
-                            umma_commit(&bars.emptyW[ws]);
-                            if (c == nck - 1) umma_commit(&bars.accFull[slot]);
                         }
-                        __syncwarp();
-                        if (lane == 0 && j == 0 && c < 4) BVC_TRACE(26 + 3 * c);
+                        if (half == 1) {
+                            umma_commit(&bars.emptyW[st.ws]);
+                            if (st.last) umma_commit(&bars.accFull[st.slot]);
+                        }
+                    }
+                    __syncwarp();
+                };
+                Step cur, nxt;
+                cur.slot = 0; cur.d_tmem = 0; nxt.slot = 0; nxt.d_tmem = 0;
+                prepare(0, 0, cur);
+                int j = 0, c = 0;
+                for (int s = 0; s < nsteps && !dead; ++s) {
+                    issue(cur, 0);
+                    int jn = j, cn = c + 1;
+                    if (cn == nck) { cn = 0; ++jn; }
+                    const bool has_next = s + 1 < nsteps;
+                    if (has_next) {
+                        nxt.slot = cur.slot; nxt.d_tmem = cur.d_tmem;     // same tile unless prepare() starts a new one
+                        prepare(jn, cn, nxt);
                     }
                     if (dead) break;
+                    issue(cur, 1);
+                    if (has_next) cur = nxt;
+                    j = jn; c = cn;
                 }
-                if (pl.n > 0 && !dead) {
+                if (!dead) {
                     if (elect_one()) umma_commit(&bars.aFree);
                     __syncwarp();
                     if (lane == 0) BVC_TRACE(7);
@@ -902,6 +925,9 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                 // acquire, before the bulk copies.  A writer-side fence.proxy.async here would be a MEMBAR.ALL.GPU in each of
                 // the epilogue threads on the critical path of every phase.
                 if (dbg_flags & 32) fence_proxy_async_all();
+                // experiment (debug flag 512): every epilogue thread fences its own stores (in parallel, right behind them)
+                // and the leader's arrival is relaxed, instead of one release-scoped arrival behind the CTA barrier
+                if (dbg_flags & 512) asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
                 {   // barrier over the 8 epilogue warps; a failed wait anywhere retires all of them together
                     uint32_t any;
                     asm volatile(
@@ -931,7 +957,8 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             }
                         }
                     }
-                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
+                    if (dbg_flags & 512) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
+                    else asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
                     BVC_TRACE(13);
                 }
             }
