@@ -44,8 +44,13 @@ SYMBOLS = {
     "bvc_logmel": (C.c_int, [_P, _P, _I, _I, _F, _P, _P]),
     "bvc_encode": (C.c_int, [_P, _P, _P, _F, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "bvc_encode_mel": (C.c_int, [_P, _P, _P, _F, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "bvc_encode_ex": (C.c_int, [_P, _P, _P, _F, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "bvc_unpack_codes": (C.c_int, [_P, _P, _P, _F, _I, _I, _P, _P]),
     "bvc_decode_mel": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P]),
+    "bvc_decode_packed": (C.c_int, [_P, _P, _P, _F, _P, _I, _I, _P, _P, _P]),
+    "bvc_bitstream_bytes": (C.c_size_t, [_P, _I, _I]),
+    "bvc_pack_bitstream": (C.c_int, [_P, _P, _P, _F, _I, _I, _P, C.c_size_t, _P]),
+    "bvc_unpack_bitstream": (C.c_int, [_P, _P, C.c_size_t, _I, _I, _P, _P, _P]),
     "bvc_vocode": (C.c_int, [_P, _P, _I, _I, _I, _F, _P, _P]),
     "bvc_vocoder_out_len": (C.c_int64, [_P, _I]),
     "bvc_encode_host": (C.c_int, [_P, _P, _I, _I, _F, _F, _P]),

@@ -192,9 +192,11 @@ class _Engine:
                        "mel_spectrogram")
         return mel
 
-    def encode(self, mel, bits, bits_scalar, h0, want_logits=False, want_all_h=True, want_packed=False, want_mel=False):
-        """-> (codes, all_h, h_final, logits, packed[, mel_hat]); mel_hat (want_mel) is the decoder's mel the encoder forms
-        inside its loop (bvrnn.py:198-206) = BVRNN.decode(codes, h0)[0]."""
+    def encode(self, mel, bits, bits_scalar, h0, want_logits=False, want_all_h=True, want_packed=False, want_mel=False,
+               uniforms=None, want_prior=False):
+        """-> (codes, all_h, h_final, logits, packed[, mel_hat][, prior]); mel_hat (want_mel) is the decoder's mel the encoder
+        forms inside its loop (bvrnn.py:198-206) = BVRNN.decode(codes, h0)[0]; uniforms [B,T,Z]: sampled bits
+        round(u - 0.5 + p) (bvrnn.py:126); prior (want_prior): the prior head's probabilities [B,T,Z] (bvrnn.py:68-73)."""
         mel = self._dev(mel, "y")
         B, T, _ = mel.shape
         dev = self.device
@@ -206,13 +208,20 @@ class _Engine:
         bits_t = self._dev(bits, "varBitrate") if bits is not None else None
         h0_t = self._dev(h0, "h") if h0 is not None else None
         mel_hat = torch.empty(B, T, self.X, device=dev, dtype=torch.float32) if want_mel else None
+        prior = torch.empty(B, T, self.Z, device=dev, dtype=torch.float32) if want_prior else None
+        u_t = self._dev(uniforms, "uniforms") if uniforms is not None else None
+        if u_t is not None and tuple(u_t.shape) != (B, T, self.Z):
+            raise ValueError(f"uniforms must have shape {(B, T, self.Z)}")
         with torch.cuda.device(dev):
-            _lib.check(self.lib.bvc_encode_mel(self.handle, _ptr(mel), _ptr(bits_t), float(bits_scalar), _ptr(h0_t), B, T,
-                                               _ptr(codes), _ptr(packed), _ptr(logits), _ptr(all_h), _ptr(h_fin),
-                                               _ptr(mel_hat), _stream(dev)), "BVRNN.encode")
+            _lib.check(self.lib.bvc_encode_ex(self.handle, _ptr(mel), _ptr(bits_t), float(bits_scalar), _ptr(h0_t), _ptr(u_t),
+                                              B, T, _ptr(codes), _ptr(packed), _ptr(logits), _ptr(all_h), _ptr(h_fin),
+                                              _ptr(mel_hat), _ptr(prior), _stream(dev)), "BVRNN.encode")
+        out = (codes, all_h, h_fin, logits, packed)
         if want_mel:
-            return codes, all_h, h_fin, logits, packed, mel_hat
-        return codes, all_h, h_fin, logits, packed
+            out = out + (mel_hat,)
+        if want_prior:
+            out = out + (prior,)
+        return out
 
     def unpack_codes(self, packed, bits, bits_scalar):
         """packed int64 [B, T] (bit i = code i) -> float codes [B, T, Z] with 0.5 for masked bits."""
@@ -222,6 +231,42 @@ class _Engine:
         _lib.check(self.lib.bvc_unpack_codes(self.handle, _ptr(packed), _ptr(bits), float(bits_scalar), B, T, _ptr(codes),
                                              _stream(self.device)), "unpack_codes")
         return codes
+
+    def decode_mel_packed(self, packed, bits, bits_scalar, h0):
+        """BVRNN.decode straight from the wire words (bvc_decode_packed): packed int64 [B, T], budgets [B, T] or a scalar."""
+        packed = packed.contiguous()
+        B, T = packed.shape
+        mel = torch.empty(B, T, self.X, device=self.device, dtype=torch.float32)
+        h_fin = torch.empty(B, self.H, device=self.device, dtype=torch.float32)
+        bits_t = self._dev(bits, "bits") if bits is not None else None
+        h0_t = self._dev(h0, "h") if h0 is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bvc_decode_packed(self.handle, _ptr(packed), _ptr(bits_t), float(bits_scalar), _ptr(h0_t), B, T,
+                                                  _ptr(mel), _ptr(h_fin), _stream(self.device)), "BVRNN.decode (packed)")
+        return mel, h_fin
+
+    def pack_bitstream(self, packed, bits, bits_scalar):
+        """words int64 [B, T] -> uint8 [B, stride] bit-streams (header + n bits per frame), see include/bvc.h."""
+        packed = packed.contiguous()
+        B, T = packed.shape
+        bits_t = self._dev(bits, "bits") if bits is not None else None
+        stride = int(self.lib.bvc_bitstream_bytes(self.handle, T, 1 if bits_t is not None else 0))
+        out = torch.empty(B, stride, device=self.device, dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bvc_pack_bitstream(self.handle, _ptr(packed), _ptr(bits_t), float(bits_scalar), B, T, _ptr(out),
+                                                   stride, _stream(self.device)), "pack_bitstream")
+        return out
+
+    def unpack_bitstream(self, stream, T):
+        """uint8 [B, stride] -> (words int64 [B, T], budgets float32 [B, T])."""
+        stream = stream.contiguous()
+        B, stride = stream.shape
+        packed = torch.empty(B, T, device=self.device, dtype=torch.int64)
+        bits = torch.empty(B, T, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bvc_unpack_bitstream(self.handle, _ptr(stream), stride, B, T, _ptr(packed), _ptr(bits),
+                                                     _stream(self.device)), "unpack_bitstream")
+        return packed, bits
 
     def decode_mel(self, codes, h0):
         codes = self._dev(codes, "z")
@@ -300,6 +345,22 @@ class _BVRNN(nn.Module):
         codes, all_h, _, _, _ = self._engine.encode(y, varBitrate, 0.0, h0)
         return codes, all_h
 
+    def encode_sampled(self, y, varBitrate, h, uniforms, want_prior=True):
+        """The sampled-bit variant of encode (reference BVRNN.forward with p_use_gen = 1, greedy = False, bvrnn.py:86-160, with
+        the uniforms of its torch.rand_like supplied by the caller): z_t = round(u_t - 0.5 + p_t).
+        -> dict(z, all_h, p = sigmoid(logits) [B,T,z_dim], prior [B,T,z_dim] or None)."""
+        h0 = h[-1] if h is not None else None
+        out = self._engine.encode(y, varBitrate, 0.0, h0, want_logits=True, uniforms=uniforms, want_prior=want_prior)
+        return dict(z=out[0], all_h=out[1], p=torch.sigmoid(out[3]), prior=out[5] if want_prior else None)
+
+    def kld(self, p, prior, varBitrate):
+        """KL(enc || prior) of the reference's training forward (bvrnn.py:148-158): host-side glue over the kernel outputs."""
+        e = p * (torch.log(torch.clip(p, 1e-3)) - torch.log(torch.clip(prior, 1e-3))) + \
+            (1 - p) * (torch.log(torch.clip(1 - p, 1e-3)) - torch.log(torch.clip(1 - prior, 1e-3)))
+        if self.varBit:
+            e = e * (varBitrate[:, :, None] > torch.arange(self.z_dim, device=p.device)[None, None, :]).float()
+        return e.sum(-1).mean(0).mean()
+
     def decode(self, z, h):
         """z (B,T,z_dim), h (1,B,h_dim) -> (mel (B,T,x_dim), h (1,B,h_dim))."""
         mel, h_fin = self._engine.decode_mel(z, h[-1] if h is not None else None)
@@ -356,17 +417,21 @@ class BVRNNCodecModel(nn.Module):
     def bits_per_frame(self, bitrate):
         return float(np.round(bitrate * self.conf['hopsize'] / self.conf['fs']))   # reference :58
 
-    def encode(self, x, bitrate):
+    def encode(self, x, bitrate, *, uniforms=None):
         '''
         x: input waveform, shape (batch, length)
         bitrate: target bitrate in bits per second, will be rounded to the nearest valid bitrate
+        uniforms (keyword-only extension): (batch, frames, z_dim) uniforms in [0, 1) -> sampled bits round(u - 0.5 + p)
+                 (the reference's stochastic mode, bvrnn.py:123-126) instead of the greedy round(p)
         '''
         bits = self.bits_per_frame(bitrate)
-        if x.device.type == "cpu":
+        if x.device.type == "cpu" and uniforms is None:
             return self._engine.encode_host(x, SCALING, bits)
-        mel = self._engine.logmel(x, SCALING)
-        codes, _, _, _, _ = self._engine.encode(mel, None, bits, None, want_all_h=False)
-        return codes
+        on_cpu = x.device.type == "cpu"
+        mel = self._engine.logmel(x.to(self.device), SCALING)
+        u = uniforms.to(self.device, torch.float32).contiguous() if uniforms is not None else None
+        codes = self._engine.encode(mel, None, bits, None, want_all_h=False, uniforms=u)[0]
+        return codes.cpu() if on_cpu else codes
 
     def decode(self, codes, length):
         '''
@@ -399,13 +464,37 @@ class BVRNNCodecModel(nn.Module):
         return packed, bits
 
     def decode_packed(self, packed, bits, length):
-        """Inverse of encode_packed: packed int64 (B, T), bits per frame (number or (B, T) tensor) -> waveform (B, length)."""
+        """Inverse of encode_packed: packed int64 (B, T), bits per frame (number or (B, T) tensor) -> waveform (B, length).
+        The words go straight into the decoder (bvc_decode_packed); the float code tensor is never formed."""
         packed = packed.to(self.device)
         if torch.is_tensor(bits):
-            codes = self._engine.unpack_codes(packed, bits.to(self.device, torch.float32).contiguous(), 0.0)
+            mel, _ = self._engine.decode_mel_packed(packed, bits.to(self.device, torch.float32).contiguous(), 0.0, None)
         else:
-            codes = self._engine.unpack_codes(packed, None, float(bits))
-        return self.decode(codes, length)
+            mel, _ = self._engine.decode_mel_packed(packed, None, float(bits), None)
+        return self._engine.vocode(mel, length, SCALING)
+
+    def encode_bitstream(self, x, bitrate):
+        """x (B, L) -> uint8 (B, n_bytes) self-describing bit-streams: 16-byte header + round(bitrate * hop / fs) bits per
+        frame (include/bvc.h; 3 kbps: 4.4 bytes per frame instead of the 256 bytes of the float codes)."""
+        packed, bits = self.encode_packed(x, bitrate)
+        return self._engine.pack_bitstream(packed, None, bits)
+
+    @staticmethod
+    def bitstream_header(stream_row):
+        """Parses the 16-byte header of one stream: dict(z_dim, mode, n_bits, T, payload_bits)."""
+        hdr = bytes(stream_row[:16].cpu().tolist())
+        if hdr[:4] != b"BVC1":
+            raise ValueError("not a BVC1 bit-stream")
+        return dict(z_dim=int.from_bytes(hdr[4:6], "little"), mode=hdr[6], n_bits=hdr[7],
+                    T=int.from_bytes(hdr[8:12], "little"), payload_bits=int.from_bytes(hdr[12:16], "little"))
+
+    def decode_bitstream(self, stream, length):
+        """Inverse of encode_bitstream (all rows must share T): uint8 (B, n_bytes) -> waveform (B, length)."""
+        stream = stream.to(self.device)
+        T = self.bitstream_header(stream[0])["T"]
+        packed, bits = self._engine.unpack_bitstream(stream, T)
+        mel, _ = self._engine.decode_mel_packed(packed, bits, 0.0, None)
+        return self._engine.vocode(mel, length, SCALING)
 
     # ---- taps used by the parity tests (not part of the reference API) ----
     def encode_with_taps(self, x, bitrate, h0=None, mel=None):

@@ -424,6 +424,7 @@ int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
     L("phi_z.0", &w.pz0, &w.b_pz0); L("phi_z.2", &w.pz2, &w.b_pz2); L("phi_z.4", &w.pz4, &w.b_pz4);
     L("enc.2", &w.e2, &w.b_e2); L("enc.4", &w.e4, &w.b_e4);
     L("dec.2", &w.d2, &w.b_d2); L("dec.4", &w.d4, &w.b_d4); L("dec.6", &w.d6, &w.b_d6);
+    L("prior.0", &w.pr0, &w.b_pr0); L("prior.2", &w.pr2, &w.b_pr2); L("prior.4", &w.pr4, &w.b_pr4);
 
     const HostTensor &e0 = m["enc.0.weight"], &d0 = m["dec.0.weight"];
     const HostTensor &wih = m["rnn.weight_ih_l0"], &whh = m["rnn.weight_hh_l0"];
@@ -523,6 +524,10 @@ int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n) {
         W(to_vec(m["phi_z.0.weight"]), Hi, Zi, 256, &rw.g_pz0);
         W(to_vec(m["phi_z.2.weight"]), Hi, Hi, 256, &rw.g_pz2);
         W(to_vec(m["phi_z.4.weight"]), Hi, Hi, 256, &rw.g_pz4);
+        W(to_vec(m["prior.0.weight"]), Hi, Hi, 256, &rw.g_pr0);
+        W(to_vec(m["prior.2.weight"]), Hi, Hi, 256, &rw.g_pr2);
+        W(to_vec(m["prior.4.weight"]), Zi, Hi, 256, &rw.g_pr4);
+        rw.b_pr4p = up(pad_to(to_vec(m["prior.4.bias"]), 256));
         void* p1 = nullptr; void* p2 = nullptr;
         ok = ok && cudaMalloc(&p1, rec::SYNC_WORDS * sizeof(unsigned)) == cudaSuccess &&
              cudaMalloc(&p2, sizeof(rec::Program)) == cudaSuccess;
@@ -812,6 +817,13 @@ int bvc_encode(bvc_handle* h, const float* mel_dev, const float* bits_dev, float
 int bvc_encode_mel(bvc_handle* h, const float* mel_dev, const float* bits_dev, float bits_scalar, const float* h0_dev,
                    int32_t B, int32_t T, float* codes_dev, uint64_t* packed_dev, float* logits_dev, float* all_h_dev,
                    float* h_final_dev, float* mel_hat_dev, void* stream) {
+    return bvc_encode_ex(h, mel_dev, bits_dev, bits_scalar, h0_dev, nullptr, B, T, codes_dev, packed_dev, logits_dev, all_h_dev,
+                         h_final_dev, mel_hat_dev, nullptr, stream);
+}
+
+int bvc_encode_ex(bvc_handle* h, const float* mel_dev, const float* bits_dev, float bits_scalar, const float* h0_dev,
+                  const float* uniforms_dev, int32_t B, int32_t T, float* codes_dev, uint64_t* packed_dev, float* logits_dev,
+                  float* all_h_dev, float* h_final_dev, float* mel_hat_dev, float* prior_dev, void* stream) {
     REQUIRE(h && mel_dev && codes_dev, BVC_ERR_INVALID, "bvc_encode: null argument");
     REQUIRE(h->have_bvrnn, BVC_ERR_STATE, "bvc_encode: BVRNN weights not loaded");
     REQUIRE(B > 0 && T >= 0, BVC_ERR_INVALID, "bvc_encode: bad B/T");
@@ -824,11 +836,19 @@ int bvc_encode_mel(bvc_handle* h, const float* mel_dev, const float* bits_dev, f
         set_error("bvc_encode: packed output needs z_dim == 64 (one uint64 word per frame)");
         return BVC_ERR_INVALID;
     }
-    if ((rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T)))) return rc;
+    const size_t n_allh = (prior_dev && !all_h_dev) ? (size_t)B * T * h->bw.H + 64 : 0;
+    if ((rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T) + n_allh))) return rc;
     if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
+    float* all_h = all_h_dev;
+    if (n_allh) all_h = h->ws.take(n_allh);       // the prior head reads the state entering every frame
+    const size_t mark = h->ws.used;
     rc = bvrnn_encode(h->bw, h->ws, mel_dev, bits_dev, bits_scalar, h0_dev, B, T, codes_dev,
-                      (unsigned long long*)packed_dev, logits_dev, all_h_dev, h_final_dev, mel_hat_dev, h->precision,
-                      (cudaStream_t)stream);
+                      (unsigned long long*)packed_dev, logits_dev, all_h, h_final_dev, mel_hat_dev, h->precision,
+                      (cudaStream_t)stream, uniforms_dev);
+    if (!rc && prior_dev) {
+        h->ws.used = mark;                         // the encoder's temporaries are dead in stream order
+        rc = bvrnn_prior(h->bw, h->ws, all_h, B, T, prior_dev, h->precision, (cudaStream_t)stream);
+    }
     const int rc2 = ws_release(h, (cudaStream_t)stream);   // also on errors: work may already be enqueued
     return rc ? rc : rc2;
 }
@@ -857,6 +877,60 @@ int bvc_decode_mel(bvc_handle* h, const float* codes_dev, const float* h0_dev, i
     if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
     rc = bvrnn_decode(h->bw, h->ws, codes_dev, h0_dev, B, T, mel_dev, h_final_dev, h->precision,
                       (cudaStream_t)stream);
+    const int rc2 = ws_release(h, (cudaStream_t)stream);
+    return rc ? rc : rc2;
+}
+
+int bvc_decode_packed(bvc_handle* h, const uint64_t* packed_dev, const float* bits_dev, float bits_scalar, const float* h0_dev,
+                      int32_t B, int32_t T, float* mel_dev, float* h_final_dev, void* stream) {
+    REQUIRE(h && packed_dev && mel_dev, BVC_ERR_INVALID, "bvc_decode_packed: null argument");
+    REQUIRE(h->have_bvrnn, BVC_ERR_STATE, "bvc_decode_packed: BVRNN weights not loaded");
+    REQUIRE(B > 0 && T >= 0, BVC_ERR_INVALID, "bvc_decode_packed: bad B/T");
+    REQUIRE(h->bw.Z <= 64, BVC_ERR_INVALID, "bvc_decode_packed: z_dim > 64 does not fit a 64-bit word");
+    if (T == 0) return BVC_OK;
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    int rc = rec_poll_aborts(h->bw.rw, false);
+    if (rc) return rc;
+    if ((rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, B, T)))) return rc;
+    if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
+    rc = bvrnn_decode(h->bw, h->ws, nullptr, h0_dev, B, T, mel_dev, h_final_dev, h->precision, (cudaStream_t)stream,
+                      (const unsigned long long*)packed_dev, bits_dev, bits_scalar);
+    const int rc2 = ws_release(h, (cudaStream_t)stream);
+    return rc ? rc : rc2;
+}
+
+size_t bvc_bitstream_bytes(const bvc_handle* h, int32_t T, int32_t per_frame_budgets) {
+    if (!h || T < 0) return 0;
+    return bitstream_bytes(T, h->cfg.z_dim, per_frame_budgets && h->cfg.var_bit);
+}
+
+int bvc_pack_bitstream(bvc_handle* h, const uint64_t* packed_dev, const float* bits_dev, float bits_scalar, int32_t B, int32_t T,
+                       uint8_t* out_dev, size_t stride, void* stream) {
+    REQUIRE(h && packed_dev && out_dev, BVC_ERR_INVALID, "bvc_pack_bitstream: null argument");
+    REQUIRE(B > 0 && T > 0, BVC_ERR_INVALID, "bvc_pack_bitstream: bad B/T");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    int rc = ensure_workspace(h, (size_t)B * (T + 1) + 256);
+    if (rc) return rc;
+    if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
+    rc = pack_bitstream(h->ws, (const unsigned long long*)packed_dev, bits_dev, bits_scalar, h->cfg.var_bit, h->cfg.z_dim, B, T,
+                        out_dev, stride, (cudaStream_t)stream);
+    const int rc2 = ws_release(h, (cudaStream_t)stream);
+    return rc ? rc : rc2;
+}
+
+int bvc_unpack_bitstream(bvc_handle* h, const uint8_t* in_dev, size_t stride, int32_t B, int32_t T, uint64_t* packed_dev,
+                         float* bits_out_dev, void* stream) {
+    REQUIRE(h && in_dev && packed_dev, BVC_ERR_INVALID, "bvc_unpack_bitstream: null argument");
+    REQUIRE(B > 0 && T > 0, BVC_ERR_INVALID, "bvc_unpack_bitstream: bad B/T");
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    int rc = ensure_workspace(h, (size_t)B * (T + 1) + 256);
+    if (rc) return rc;
+    if ((rc = ws_acquire(h, (cudaStream_t)stream))) return rc;
+    rc = unpack_bitstream(h->ws, in_dev, stride, B, T, h->cfg.z_dim, (unsigned long long*)packed_dev, bits_out_dev,
+                          (cudaStream_t)stream);
     const int rc2 = ws_release(h, (cudaStream_t)stream);
     return rc ? rc : rc2;
 }

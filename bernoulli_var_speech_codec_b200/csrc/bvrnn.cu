@@ -30,7 +30,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 bottleneck_kernel(const float* __restrict__ logit, int B, int Z, int T, int t, const float* __restrict__ bits,
                   float bits_scalar, int var_bit, float* __restrict__ codes, uint32_t* __restrict__ packed,
-                  float* __restrict__ logits_out) {
+                  float* __restrict__ logits_out, const float* __restrict__ uniforms) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = idx / Z, i = idx - b * Z;
     const bool valid = b < B;
@@ -39,7 +39,7 @@ bottleneck_kernel(const float* __restrict__ logit, int B, int Z, int T, int t, c
     if (valid) {
         lg = logit[idx];
         const float p = sigmoidf_(lg);
-        bit = p > 0.5f;
+        bit = uniforms ? (rintf((uniforms[((size_t)b * T + t) * Z + i] - 0.5f) + p) == 1.f) : (p > 0.5f);   // bvrnn.py:126 / :191
         const float budget = bits ? bits[(size_t)b * T + t] : bits_scalar;
         const bool active = !var_bit || (budget > (float)i);
         bit = bit && active;
@@ -70,6 +70,11 @@ gru_gate_kernel(const float* __restrict__ gi, int ldgi, const float* __restrict_
     const float hv = h[idx];
     if (all_h) all_h[((size_t)b * T + t) * H + j] = hv;   // state entering frame t (bvrnn.py:205)
     h_next[idx] = (hv - n) * z + n;
+}
+
+__global__ void sigmoid_kernel(float* __restrict__ x, size_t n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) x[idx] = sigmoidf_(x[idx]);
 }
 
 __global__ void normalize_kernel(const float* __restrict__ y, const float* __restrict__ mean,
@@ -138,12 +143,13 @@ size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T) {
     n += 2 * (BTp * H + 64);            // two hoisted activation buffers (images: hi + lo bf16 = 4 bytes per element)
     n += BT * 4 * H + 64;               // hoisted fp32 output: encode [B*T, H], decode [dec.0_z ; W_ih_z] . phi_z [B*T, 4H]
     n += Bp * (40 * H + 2 * w.X + 2 * w.Z + 256) + 64 * 64;
+    n += BT * w.Z + BT + (size_t)B + 128;   // packed decode on the layer path (expanded codes); bit-stream offset tables
     return n;
 }
 
 static int bvrnn_encode_layers(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
-                 float* all_h, float* h_final, int precision, cudaStream_t s) {
+                 float* all_h, float* h_final, int precision, cudaStream_t s, const float* uniforms) {
     const int H = w.H, X = w.X, Z = w.Z;
     const size_t BT = (size_t)B * T;
     if (BT > (size_t)INT32_MAX / 4) { set_error("B*T too large"); return BVC_ERR_INVALID; }
@@ -193,7 +199,7 @@ static int bvrnn_encode_layers(BvrnnWeights& w, Workspace& ws, const float* mel,
         BVC_TRY(run_linear(hg, 5 * H, B, w.e2, w.b_e2, H, e2, H, precision, s));
         BVC_TRY(run_linear(e2, H, B, w.e4, w.b_e4, 0, lg, Z, precision, s));
         bottleneck_kernel<<<(B * Z + 255) / 256, 256, 0, s>>>(lg, B, Z, T, t, bits, bits_scalar, w.var_bit, codes,
-                                                            reinterpret_cast<uint32_t*>(packed), logits);
+                                                            reinterpret_cast<uint32_t*>(packed), logits, uniforms);
         BVC_CHECK_LAUNCH();
         // phi_z(z_t)                                                        (bvrnn.py:198)
         BVC_TRY(run_linear(codes + (size_t)t * Z, TZ, B, w.pz0, w.b_pz0, H, z1, H, precision, s));
@@ -408,10 +414,7 @@ int acquire_slot(RecurrentWeights& rw, int kind, rec::Program** out) {
 // Enqueues program upload, the persistent kernel and the read-back of its abort flag; no host synchronisation.
 int run_program(BvrnnWeights& w, ProgramBuilder& pb, cudaStream_t s) {
     RecurrentWeights::ProgSlot& sl = w.rw.slots[w.rw.cur_slot];
-    if (const char* e = getenv("BVC_REC_DEBUG")) {
-        pb.p->debug_flags = atoi(e);
-        pb.p->frame.pad_ = (pb.p->debug_flags & 256) ? 1 : 0;      // timing probe: skip the activation-image stores (wrong results)
-    }
+    if (const char* e = getenv("BVC_REC_DEBUG")) pb.p->debug_flags = atoi(e);
     if (!pb.finish()) {
         set_error("recurrent program does not fit the static limits (m-tiles / entries)");
         return BVC_ERR_INVALID;
@@ -539,7 +542,7 @@ static int persistent_max_rows(int n_clusters) {
 static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits,
                                    float bits_scalar, const float* h0, int B, int T, float* codes,
                                    unsigned long long* packed, float* logits, float* all_h, float* h_final,
-                                   float* mel_hat, cudaStream_t s) {
+                                   float* mel_hat, cudaStream_t s, const float* uniforms) {
     const int H = w.H, X = w.X, Z = w.Z;
     const size_t BT = (size_t)B * T;
     RecurrentWeights& rw = w.rw;
@@ -577,7 +580,7 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     rec::Frame& fr = p->frame;
     fr.M = B; fr.T = T; fr.X = X; fr.Z = Z; fr.H = H; fr.var_bit = w.var_bit;
     fr.bits_scalar = bits_scalar; fr.bits = bits; fr.codes = codes; fr.packed = packed; fr.logits = logits;
-    fr.all_h = all_h; fr.h = hf; fr.h_img = hI; fr.gh = gh; fr.mel_out = mel_hat;
+    fr.all_h = all_h; fr.h = hf; fr.h_img = hI; fr.gh = gh; fr.mel_out = mel_hat; fr.uniforms = uniforms;
 
     ProgramBuilder pb;
     pb.p = p; pb.n_clusters = G; pb.M = B;
@@ -646,7 +649,8 @@ static int bvrnn_encode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
 }
 
 static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T,
-                                   float* mel, float* h_final, cudaStream_t s) {
+                                   float* mel, float* h_final, cudaStream_t s, const unsigned long long* packed,
+                                   const float* bits, float bits_scalar) {
     const int H = w.H, X = w.X, Z = w.Z;
     const size_t BT = (size_t)B * T;
     RecurrentWeights& rw = w.rw;
@@ -666,7 +670,8 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
     BVC_TRY(ws_check(ws, "BVRNN.decode"));
 
     // hoisted over all frames (tcgen05 GEMMs): phi_z(z), then [dec.0_z ; W_ih_z (gate-interleaved)] . phi_z + [b_d0 ; b_ih]
-    BVC_TRY(to_image(codes, (int)BT, Z, nullptr, nullptr, zI_all, Z / rec::CHUNK_K, s));
+    if (codes) BVC_TRY(to_image(codes, (int)BT, Z, nullptr, nullptr, zI_all, Z / rec::CHUNK_K, s));
+    else BVC_TRY(words_to_image(packed, bits, bits_scalar, w.var_bit, (int)BT, zI_all, s));    // wire words straight to the operand image
     BVC_TRY(linear_umma(zI_all, (int)BT, rw.g_pz0, w.b_pz0, 1, nullptr, 0, PAi, s));
     BVC_TRY(linear_umma(PAi, (int)BT, rw.g_pz2, w.b_pz2, 1, nullptr, 0, PBi, s));
     BVC_TRY(linear_umma(PBi, (int)BT, rw.g_pz4, w.b_pz4, 1, nullptr, 0, PAi, s));
@@ -717,11 +722,11 @@ static int bvrnn_decode_persistent(BvrnnWeights& w, Workspace& ws, const float* 
 
 int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
-                 float* all_h, float* h_final, float* mel_hat, int precision, cudaStream_t s) {
+                 float* all_h, float* h_final, float* mel_hat, int precision, cudaStream_t s, const float* uniforms) {
     if (!(precision >= 1 && w.rw.ready)) {
         const size_t mark = ws.used;
         BVC_TRY(bvrnn_encode_layers(w, ws, mel, bits, bits_scalar, h0, B, T, codes, packed, logits, all_h, h_final,
-                                    precision, s));
+                                    precision, s, uniforms));
         if (mel_hat) {      // the layer-by-layer path keeps the second recurrence (same result, bvrnn.py:198-206 vs 222-227)
             ws.used = mark;
             BVC_TRY(bvrnn_decode_layers(w, ws, codes, h0, B, T, mel_hat, nullptr, precision, s));
@@ -741,14 +746,59 @@ int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* 
                                         h0 ? h0 + r * w.H : nullptr, nb, T, codes + r * T_ * w.Z,
                                         packed ? packed + r * T_ : nullptr, logits ? logits + r * T_ * w.Z : nullptr,
                                         all_h ? all_h + r * T_ * w.H : nullptr, h_final ? h_final + r * w.H : nullptr,
-                                        mel_hat ? mel_hat + r * T_ * w.X : nullptr, s));
+                                        mel_hat ? mel_hat + r * T_ * w.X : nullptr, s,
+                                        uniforms ? uniforms + r * T_ * w.Z : nullptr));
     }
     return BVC_OK;
 }
 
+// prior(h) = sigmoid(W4 ELU(W2 ELU(W0 h + b0) + b2) + b4) over all B*T states: three hoisted GEMMs (no recurrence)
+int bvrnn_prior(BvrnnWeights& w, Workspace& ws, const float* all_h, int B, int T, float* prior, int precision, cudaStream_t s) {
+    const size_t BT = (size_t)B * T;
+    const int H = w.H, Z = w.Z;
+    const size_t mark = ws.used;
+    int rc = BVC_OK;
+    if (precision >= 1 && w.rw.ready) {
+        unsigned char* hI = take_img(ws, (int)BT, H);
+        unsigned char* aI = take_img(ws, (int)BT, H);
+        rc = ws_check(ws, "BVRNN prior");
+        if (!rc) rc = to_image(all_h, (int)BT, H, nullptr, nullptr, hI, H / rec::CHUNK_K, s);
+        if (!rc) rc = linear_umma(hI, (int)BT, w.rw.g_pr0, w.b_pr0, 1, nullptr, 0, aI, s);
+        if (!rc) rc = linear_umma(aI, (int)BT, w.rw.g_pr2, w.b_pr2, 1, nullptr, 0, hI, s);
+        if (!rc) rc = linear_umma(hI, (int)BT, w.rw.g_pr4, w.rw.b_pr4p, 2, prior, Z, nullptr, s);
+    } else {
+        float* a = ws.take(BT * H);
+        float* b = ws.take(BT * H);
+        rc = ws_check(ws, "BVRNN prior (layer path)");
+        if (!rc) rc = run_linear(all_h, H, (int)BT, w.pr0, w.b_pr0, H, a, H, precision, s);
+        if (!rc) rc = run_linear(a, H, (int)BT, w.pr2, w.b_pr2, H, b, H, precision, s);
+        if (!rc) rc = run_linear(b, H, (int)BT, w.pr4, w.b_pr4, 0, prior, Z, precision, s);
+        if (!rc) {
+            const size_t n = BT * Z;
+            sigmoid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(prior, n);
+            if (g_launch_counter) ++*g_launch_counter;
+            if (cudaGetLastError() != cudaSuccess) { set_error("sigmoid kernel launch failed"); rc = BVC_ERR_DEVICE; }
+        }
+    }
+    ws.used = mark;
+    return rc;
+}
+
 int bvrnn_decode(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T, float* mel,
-                 float* h_final, int precision, cudaStream_t s) {
-    if (!(precision >= 1 && w.rw.ready)) return bvrnn_decode_layers(w, ws, codes, h0, B, T, mel, h_final, precision, s);
+                 float* h_final, int precision, cudaStream_t s, const unsigned long long* packed, const float* bits,
+                 float bits_scalar) {
+    if (!(precision >= 1 && w.rw.ready)) {
+        const size_t mark0 = ws.used;
+        if (!codes) {      // the layer-by-layer path works on float codes: expand the words first
+            float* tmp = ws.take((size_t)B * T * w.Z);
+            BVC_TRY(ws_check(ws, "BVRNN.decode (packed)"));
+            BVC_TRY(unpack_codes(packed, bits, bits_scalar, w.var_bit, (size_t)B * T, w.Z, tmp, s));
+            codes = tmp;
+        }
+        const int rc = bvrnn_decode_layers(w, ws, codes, h0, B, T, mel, h_final, precision, s);
+        ws.used = mark0;
+        return rc;
+    }
     int G = 0;
     BVC_TRY(cluster_count(&G));
     const int max_rows = persistent_max_rows(G);
@@ -758,8 +808,9 @@ int bvrnn_decode(BvrnnWeights& w, Workspace& ws, const float* codes, const float
         const int nb = B - b0 < max_rows ? B - b0 : max_rows;
         const size_t r = (size_t)b0;
         ws.used = mark;
-        BVC_TRY(bvrnn_decode_persistent(w, ws, codes + r * T_ * w.Z, h0 ? h0 + r * w.H : nullptr, nb, T,
-                                        mel + r * T_ * w.X, h_final ? h_final + r * w.H : nullptr, s));
+        BVC_TRY(bvrnn_decode_persistent(w, ws, codes ? codes + r * T_ * w.Z : nullptr, h0 ? h0 + r * w.H : nullptr, nb, T,
+                                        mel + r * T_ * w.X, h_final ? h_final + r * w.H : nullptr, s,
+                                        packed ? packed + r * T_ : nullptr, bits ? bits + r * T_ : nullptr, bits_scalar));
     }
     return BVC_OK;
 }

@@ -107,6 +107,8 @@ struct RecurrentWeights {
     // hoisted layers (gemm_umma.cu), weight images with bn = 256; g_zcat = [dec.0[:, :H]; W_ih[:, H:] gate-interleaved]
     WImg g_px0, g_px2, g_px4, g_e0x, g_pz0, g_pz2, g_pz4, g_zcat;
     float* b_zcat_q = nullptr;
+    WImg g_pr0, g_pr2, g_pr4;        // prior head (bvrnn.py:68-73), evaluated over all frames from all_h
+    float* b_pr4p = nullptr;         // prior.4 bias padded to the 256-wide tile
     unsigned* sync_words = nullptr;  // device: abort flag + one barrier counter per m-tile
     rec::Program* prog_dev = nullptr;
     // Launches are asynchronous: a ring of pinned staging slots (program image + the kernel's abort flag read back after
@@ -146,6 +148,8 @@ struct BvrnnWeights {
     LinearWeights hcat_dec;           // [dec.0[:,H:]; W_hh]                N = 4H   (input h)
     LinearWeights zcat;               // [dec.0[:,:H]; W_ih[:,H:]]          N = 4H   (input phi_z)
     LinearWeights ihx;                // W_ih[:, :H]                        N = 3H   (input phi_x_gen)
+    LinearWeights pr0, pr2, pr4;      // prior head
+    float *b_pr0 = nullptr, *b_pr2 = nullptr, *b_pr4 = nullptr;
     float *b_px0, *b_px2, *b_px4, *b_pz0, *b_pz2, *b_pz4, *b_e2, *b_e4, *b_d2, *b_d4, *b_d6;
     float *b_hcat_enc, *b_hcat_dec, *b_zcat;
     RecurrentWeights rw;
@@ -182,11 +186,26 @@ inline int device_slot() {
 size_t bvrnn_workspace_floats(const BvrnnWeights& w, int B, int T);
 int unpack_codes(const unsigned long long* packed, const float* bits, float bits_scalar, int var_bit, size_t n_frames,
                  int Z, float* codes, cudaStream_t s);
+// packed wire format (wire.cu)
+size_t bitstream_bytes(int T, int Z, int per_frame);
+int pack_bitstream(Workspace& ws, const unsigned long long* words, const float* bits, float bits_scalar, int var_bit, int Z,
+                   int B, int T, unsigned char* out, size_t stride, cudaStream_t s);
+int unpack_bitstream(Workspace& ws, const unsigned char* in, size_t stride, int B, int T, int Z, unsigned long long* words,
+                     float* bits_out, cudaStream_t s);
+int words_to_image(const unsigned long long* words, const float* bits, float bits_scalar, int var_bit, int M,
+                   unsigned char* img, cudaStream_t s);
+// uniforms [B,T,Z] (nullable): sampled bits z = round(u - 0.5 + p) instead of round(p) (bvrnn.py:123-126)
 int bvrnn_encode(BvrnnWeights& w, Workspace& ws, const float* mel, const float* bits, float bits_scalar,
                  const float* h0, int B, int T, float* codes, unsigned long long* packed, float* logits,
-                 float* all_h, float* h_final, float* mel_hat, int precision, cudaStream_t stream);
+                 float* all_h, float* h_final, float* mel_hat, int precision, cudaStream_t stream,
+                 const float* uniforms = nullptr);
+// prior(h_t) for all frames: all_h [B,T,H] -> probabilities [B,T,Z] (bvrnn.py:68-73,115-120)
+int bvrnn_prior(BvrnnWeights& w, Workspace& ws, const float* all_h, int B, int T, float* prior, int precision,
+                cudaStream_t stream);
+// codes [B,T,Z] floats, or (codes == nullptr) packed words [B,T] + budgets (bits [B,T] or bits_scalar)
 int bvrnn_decode(BvrnnWeights& w, Workspace& ws, const float* codes, const float* h0, int B, int T,
-                 float* mel, float* h_final, int precision, cudaStream_t stream);
+                 float* mel, float* h_final, int precision, cudaStream_t stream,
+                 const unsigned long long* packed = nullptr, const float* bits = nullptr, float bits_scalar = 0.f);
 
 // ---------------------------------------------------------------------------
 // causal BigVGAN-tiny vocoder (vocoder.cu)
@@ -258,7 +277,14 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
 // tensor-core epilogues: ex2.approx based; absolute error <= ~1.2e-7 for v <= 0 (expm1f costs ~0.7 us per layer on the
 // recurrence's critical path: 16 serial evaluations per epilogue thread)
-__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+// (ex2.approx.ftz directly: __expf adds a denormal-range rescue of ~10 predicated instructions per value, and exp(v) - 1 is
+// -1 to fp32 precision long before that range)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : ex2_ftz(v * 1.4426950408889634f) - 1.f; }
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 __device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 // tanh(v) = 1 - 2 / (1 + e^{2v}); saturates correctly: e^{2v} -> inf gives 1, -> 0 gives -1

@@ -220,9 +220,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(GemmArgs a) {
                     v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
                 }
             }
-            if (a.act) {
+            if (a.act == 1) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
+            } else if (a.act == 2) {      // Bernoulli probabilities of the prior head (bvrnn.py:68-73)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = sigmoidf_(v[i]);
             }
             if (a.out_img && col0 < a.N) store_img16(a.out_img, m_tile, a.out_kchunks, row, col0, v);
             if (a.out_f) {

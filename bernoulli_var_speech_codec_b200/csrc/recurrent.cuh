@@ -72,6 +72,7 @@ struct Frame {
     unsigned char* h_img;          // activation images of h
     const float* gh;               // [M][3H] W_hh h + b_hh, gate-interleaved columns
     float* mel_out;                // [M][T][X] or null
+    const float* uniforms;         // [M][T][Z] or null: sampled bits round(u - 0.5 + p) (bvrnn.py:126)
 };
 
 // A frame = n_phases phases.  Cluster c works on m-tile cluster_mtile[c]; in phase p it executes the entries

@@ -41,9 +41,12 @@ constexpr int kThreads = 384;                                // MMA warp, copy w
 constexpr int A_SLOTS = 4;                                   // chunks of the resident activation quarter
 constexpr int W_SLOTS = 4;
 constexpr int W_SLOT_BYTES = 2 * 64 * 128;                   // bn <= 64
-constexpr int ACC_SLOTS = 8;
+constexpr int ACC_SLOTS = 4;
 constexpr int ACC_COLS = 64;
-constexpr int TMEM_COLS = ACC_SLOTS * ACC_COLS;              // 512: the whole tensor memory of the SM
+constexpr int TMEM_COLS = 512;                               // the whole tensor memory of the SM:
+constexpr int TMEM_A_HI = ACC_SLOTS * ACC_COLS;              //   columns 0 .. 255 accumulator slots, 256 .. 383 the hi part and
+constexpr int TMEM_A_LO = TMEM_A_HI + 128;                   //   384 .. 511 the lo part of the resident activation quarter
+                                                             //   (128 rows x 256 K as bf16 pairs: 8 columns per k16 step)
 constexpr int STG_SENDER_BYTES = 4 * TILE_M * 16;            // [4 column quads][128 rows][16 bytes]
 constexpr int STG_BUF_BYTES = (CLUSTER - 1) * STG_SENDER_BYTES;
 constexpr int SMEM_A = 0;
@@ -202,12 +205,26 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
         : "memory");
 }
 
+// A operand from tensor memory (lane = row, 8 columns per k16 step), B from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared -> tensor memory: 128 rows x 32 bytes (one k16 step of a K-major SWIZZLE_128B operand, addressed by the MMA's own
+// descriptor) into 8 columns; runs in the tensor pipe, in issue order with the MMAs of the same thread
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
+
+// two fp32 values -> packed bf16 pairs (x = hi + lo), one packed conversion per part (cvt.rn.bf16x2.f32 d, hi_half, lo_half)
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -413,18 +430,27 @@ __device__ __forceinline__ void prefetch8(const Op& op, const Frame& fr, int t, 
 }
 // Epilogue of 8 output columns (col0 .. col0+7) of row m.  v = A.W^T summed over the whole K.
 __device__ __forceinline__ void finalize8(const Op& op, const Frame& fr, int t, int m, int row, int m_tile, int col0, float* v,
-                                          const Prefetch8& pf) {
+                                          const Prefetch8& pf, unsigned long long* tr = nullptr) {
     if (m >= fr.M) return;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += pf.a[i];
+    if (tr) tr[20] = (unsigned long long)clock64();
     if (op.kind == KIND_BOTTLENECK) {
         // z = round(sigmoid(logit)), masked to 0.5 beyond the frame's bit budget (bvrnn.py:191-196)
         float code[8];
         uint32_t word = 0;
+        float u[8];
+        if (fr.uniforms) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(fr.uniforms + ((size_t)m * fr.T + t) * fr.Z + col0));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(fr.uniforms + ((size_t)m * fr.T + t) * fr.Z + col0) + 1);
+            u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = b.x; u[5] = b.y; u[6] = b.z; u[7] = b.w;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const bool active = !fr.var_bit || (pf.budget > (float)(col0 + i));
-            const bool bit = active && (sigmoidf_(v[i]) > 0.5f);
+            // greedy: round(p) (half to even: p == 0.5 -> 0);  sampled: round((u - 0.5) + p) in the reference's fp32 order
+            const float p = sigmoidf_(v[i]);
+            const bool bit = active && (fr.uniforms ? (rintf((u[i] - 0.5f) + p) == 1.f) : (p > 0.5f));
             code[i] = active ? (bit ? 1.f : 0.f) : 0.5f;
             if (bit) word |= 1u << i;
         }
@@ -439,6 +465,7 @@ __device__ __forceinline__ void finalize8(const Op& op, const Frame& fr, int t, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = elu_fast(v[i]);
     }
+    if (tr) tr[21] = (unsigned long long)clock64();
     if (op.kind == KIND_MEL) {
         if (fr.mel_out) {
             float* mo = fr.mel_out + ((size_t)m * fr.T + t) * fr.X;
@@ -449,8 +476,10 @@ __device__ __forceinline__ void finalize8(const Op& op, const Frame& fr, int t, 
         }
         return;
     }
-    if (op.out_img && col0 < op.N && !(fr.pad_ & 1)) store_img8(op.out_img, m_tile, op.out_kchunks, row, col0, v, false);
+    if (op.out_img && col0 < op.N) store_img8(op.out_img, m_tile, op.out_kchunks, row, col0, v, false);
+    if (tr) tr[22] = (unsigned long long)clock64();
     if (op.out_f && col0 < op.N) store8(op.out_f + (size_t)m * op.ldo + col0, v);
+    if (tr) tr[23] = (unsigned long long)clock64();
 }
 // Reduce-scatter of a 128 x 64 partial tile with two threads per row: acc = this thread's 8 columns of each of the four
 // quarters (quarter p at acc[8 p]); staging quads 2 hf, 2 hf + 1 of every sender belong to column half hf.
@@ -605,8 +634,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     const uint32_t bytes = 2u * op.bn * 128u;
                     const unsigned char* src = op.w_img + ((size_t)nt * pl.k_chunks + pl.kc0 + c) * bytes;
                     if (elect_one()) {
-                        mbar_expect_tx(&bars.fullW[slot], bytes);
-                        bulk_g2s(smem_base + SMEM_W + slot * W_SLOT_BYTES, src, bytes, &bars.fullW[slot]);
+                        if (dbg_flags & 4096) mbar_arrive(&bars.fullW[slot]);      // timing probe (wrong results): no weight copy
+                        else {
+                            mbar_expect_tx(&bars.fullW[slot], bytes);
+                            bulk_g2s(smem_base + SMEM_W + slot * W_SLOT_BYTES, src, bytes, &bars.fullW[slot]);
+                        }
                     }
                     __syncwarp();
                     ++wIt;
@@ -658,106 +690,118 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                                  // memory, and with ~28 KiB of L1 left next to 228 KiB of shared memory its loads come back from L2)
         bool dead = false;
         const uint64_t descA = make_desc(smem_base + SMEM_A), descW = make_desc(smem_base + SMEM_W);
-        // One "step" = the MMAs of one 64-wide K chunk of one tile.  The tensor pipe executes in order and its queue is short:
-        // whenever this warp is away from the issue slot for longer than the one or two MMAs still queued (a barrier wait is
-        // 100 - 400 clk), the pipe idles.  Measured in place (profiles/r02_recurrent_trace_clk_*.txt): 860 clk per chunk for
-        // 460 clk of MMA execution.  So the loop is software-pipelined: the waits for the NEXT step (activation chunk, weight
-        // chunk, accumulator slot) are taken in the MIDDLE of the current step's MMAs, while the first half of them executes.
-        struct Step {
-            uint32_t d_tmem, idesc, idesc2, ws, slot, bnw;     // bnw: byte offset (>> 4) of the lo rows inside a weight slot
-            int c;
-            bool stacked, last;
-        };
         for (int t = 0; t < T && !dead; ++t) {
             for (int ph = 0; ph < n_phases && !dead; ++ph) {
                 const PhaseLocal& pl = ctl.ph[ph];
                 const int nck = pl.nck;
-                const int nsteps = pl.n * nck;
-                if (nsteps == 0) continue;
-                // waits for everything step (j, c) reads; fills `st`
-                auto prepare = [&](int j, int c, Step& st) {
-                    {
-                        const uint32_t e = ctl.ent[pl.e_off + j];
-                        const Op& op = ctl.ops[e >> 8];
-                        st.stacked = op.stack != 0;
-                        st.idesc = make_idesc(TILE_M, op.bn);
-                        st.idesc2 = make_idesc(TILE_M, 2 * op.bn);
-                        st.bnw = (uint32_t)((op.bn * 128) >> 4);
-                    }
-                    if (c == 0) {
-                        if (st.stacked && (accIt & 1)) ++accIt;
-                        st.slot = accIt % ACC_SLOTS;
-                        accIt += st.stacked ? 2 : 1;
-                        for (int q = 0; q < (st.stacked ? 2 : 1) && !dead; ++q) {
-                            const uint32_t bit = 1u << (st.slot + q);
-                            if ((accUsed & bit) && !mbar_wait<false>(&bars.accEmpty[st.slot + q], (accPar >> (st.slot + q)) & 1u, abort_flag, 21)) dead = true;
-                            if (accUsed & bit) accPar ^= bit;
-                            accUsed |= bit;
-                        }
-                        st.d_tmem = tmem + st.slot * ACC_COLS;
-                    }
-                    st.c = c;
-                    st.last = c == nck - 1;
-                    if (j == 0 && !dead) {
-                        if (!mbar_wait<false>(&bars.fullA[c], (aPar >> c) & 1u, abort_flag, 22)) dead = true;
-                        aPar ^= 1u << c;
-                        if (lane == 0 && c == 0) BVC_TRACE(5);
-                        if (lane == 0 && c == nck - 1) BVC_TRACE(6);
-                    }
-                    st.ws = wIt % W_SLOTS;
-                    if (!dead && !mbar_wait<false>(&bars.fullW[st.ws], (wIt / W_SLOTS) & 1u, abort_flag, 23)) dead = true;
-                    ++wIt;
-                    tc_fence_after();
-                };
-                // k16 steps [2 half, 2 half + 1] of a step; the second half also releases the weight slot / completes the accumulator
-                auto issue = [&](const Step& st, int half) {
-                    if (elect_one()) {
-                        const uint64_t dah = descA + (uint64_t)((st.c * ACT_CHUNK_BYTES) >> 4);
-                        const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
-                        const uint64_t dwh = descW + (uint64_t)((st.ws * W_SLOT_BYTES) >> 4);
-                        const uint64_t dwl = dwh + (uint64_t)st.bnw;
-                        if (st.stacked) {
-#pragma unroll
-                            for (int k2 = 0; k2 < 2; ++k2) {
-                                const int ks = 2 * half + k2;
-                                umma(st.d_tmem, dah + 2 * ks, dwh + 2 * ks, st.idesc2, (st.c | ks) != 0 ? 1u : 0u);
-                                umma(st.d_tmem, dal + 2 * ks, dwh + 2 * ks, st.idesc, 1u);
-                            }
-                        } else {
-#pragma unroll
-                            for (int k2 = 0; k2 < 2; ++k2) {   // small terms first
-                                const int ks = 2 * half + k2;
-                                umma(st.d_tmem, dal + 2 * ks, dwh + 2 * ks, st.idesc, (st.c | ks) != 0 ? 1u : 0u);
-                                umma(st.d_tmem, dah + 2 * ks, dwl + 2 * ks, st.idesc, 1u);
-                                umma(st.d_tmem, dah + 2 * ks, dwh + 2 * ks, st.idesc, 1u);
-                            }
-                        }
-                        if (half == 1) {
-                            umma_commit(&bars.emptyW[st.ws]);
-                            if (st.last) umma_commit(&bars.accFull[st.slot]);
-                        }
-                    }
-                    __syncwarp();
-                };
-                Step cur, nxt;
-                cur.slot = 0; cur.d_tmem = 0; nxt.slot = 0; nxt.d_tmem = 0;
-                prepare(0, 0, cur);
-                int j = 0, c = 0;
-                for (int s = 0; s < nsteps && !dead; ++s) {
-                    issue(cur, 0);
-                    int jn = j, cn = c + 1;
-                    if (cn == nck) { cn = 0; ++jn; }
-                    const bool has_next = s + 1 < nsteps;
-                    if (has_next) {
-                        nxt.slot = cur.slot; nxt.d_tmem = cur.d_tmem;     // same tile unless prepare() starts a new one
-                        prepare(jn, cn, nxt);
+                // A CTA with several tiles in the phase reads its activation quarter once per tile.  The MMA stage is bound by
+                // shared-memory bandwidth (operand fetch of the MMAs + the bulk copies landing: measured in place at twice the
+                // isolated MMA time, tools/umma_bench.cu), and the 128 x 16 activation operand is the larger part of every fetch.
+                // Such a phase copies each activation chunk to tensor memory once (tcgen05.cp, 8 per chunk) and issues the MMAs
+                // of ALL its tiles with the A operand from tensor memory: shared memory then only serves the weights.  Same
+                // products in the same order, so the results are identical to the shared-memory form.
+                const bool use_ts = pl.n >= 2 && nck == 4 && !(dbg_flags & 1024);
+                for (int j = 0; j < pl.n && !dead; ++j) {
+                    const uint32_t e = ctl.ent[pl.e_off + j];
+                    const int bn = ctl.ops[e >> 8].bn;
+                    // A CTA with a single tile in this phase (the regular, latency-bound phases) has tensor memory to spare: it
+                    // issues a_hi x [w_hi | w_lo] as ONE MMA of width 2 bn into [main | aux] (the weight image already stores
+                    // the lo rows right behind the hi rows) plus a_lo x w_hi, i.e. two activation fetches per k16 step instead
+                    // of three, and takes two adjacent accumulator slots for it.  The epilogue adds main + aux.
+                    const bool stacked = ctl.ops[e >> 8].stack != 0;
+                    if (stacked && (accIt & 1)) ++accIt;
+                    const int slot = accIt % ACC_SLOTS;
+                    accIt += stacked ? 2 : 1;
+                    for (int q = 0; q < (stacked ? 2 : 1) && !dead; ++q) {
+                        const uint32_t bit = 1u << (slot + q);
+                        if ((accUsed & bit) && !mbar_wait<false>(&bars.accEmpty[slot + q], (accPar >> (slot + q)) & 1u, abort_flag, 21)) dead = true;
+                        if (accUsed & bit) accPar ^= bit;
+                        accUsed |= bit;
                     }
                     if (dead) break;
-                    issue(cur, 1);
-                    if (has_next) cur = nxt;
-                    j = jn; c = cn;
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc(TILE_M, bn), idesc2 = make_idesc(TILE_M, 2 * bn);
+                    const uint32_t d_tmem = tmem + slot * ACC_COLS;
+                    // The tensor pipe runs dry whenever this warp is not issuing (an MMA issues in ~55 clk and executes in ~72), so
+                    // the chunks that have already landed are found with one batch of polls instead of one blocking wait each.
+                    uint32_t okW = 0, okA = j == 0 ? 0u : 0xFu;
+#pragma unroll
+                    for (int i = 0; i < A_SLOTS; ++i)
+                        if (i < nck) okW |= mbar_test(&bars.fullW[(wIt + i) % W_SLOTS], ((wIt + i) / W_SLOTS) & 1u) << i;
+                    for (int c = 0; c < nck; ++c) {
+                        if (j == 0) {
+                            if (!((okA >> c) & 1u) && !mbar_wait<false>(&bars.fullA[c], (aPar >> c) & 1u, abort_flag, 22)) { dead = true; break; }
+                            if (c == 0) {
+#pragma unroll
+                                for (int i = 1; i < A_SLOTS; ++i)
+                                    if (i < nck) okA |= mbar_test(&bars.fullA[i], (aPar >> i) & 1u) << i;
+                            }
+                            aPar ^= 1u << c;
+                            if (lane == 0 && c == 0) BVC_TRACE(5);
+                            if (lane == 0 && c == nck - 1) BVC_TRACE(6);
+                        }
+                        const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
+                        if (!((okW >> c) & 1u) && !mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
+                        ++wIt;
+                        tc_fence_after();
+                        if (use_ts) {
+                            if (elect_one()) {
+                                const uint64_t dah = descA + (uint64_t)((c * ACT_CHUNK_BYTES) >> 4);
+                                const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
+                                const uint64_t dwh = descW + (uint64_t)((ws * W_SLOT_BYTES) >> 4);
+                                const uint64_t dwl = dwh + (uint64_t)((bn * 128) >> 4);
+                                const uint32_t th = tmem + TMEM_A_HI + c * 32, tl = tmem + TMEM_A_LO + c * 32;
+                                if (j == 0) {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) {
+                                        tmem_cp_128x256b(th + 8 * ks, dah + 2 * ks);
+                                        tmem_cp_128x256b(tl + 8 * ks, dal + 2 * ks);
+                                    }
+                                }
+                                if (stacked) {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) {
+                                        umma_ts(d_tmem, th + 8 * ks, dwh + 2 * ks, idesc2, (c | ks) != 0 ? 1u : 0u);
+                                        umma_ts(d_tmem, tl + 8 * ks, dwh + 2 * ks, idesc, 1u);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) {   // small terms first
+                                        umma_ts(d_tmem, tl + 8 * ks, dwh + 2 * ks, idesc, (c | ks) != 0 ? 1u : 0u);
+                                        umma_ts(d_tmem, th + 8 * ks, dwl + 2 * ks, idesc, 1u);
+                                        umma_ts(d_tmem, th + 8 * ks, dwh + 2 * ks, idesc, 1u);
+                                    }
+                                }
+                                umma_commit(&bars.emptyW[ws]);
+                                if (c == nck - 1) umma_commit(&bars.accFull[slot]);
+                            }
+                        } else if (elect_one()) {
+                            const uint64_t dah = descA + (uint64_t)((c * ACT_CHUNK_BYTES) >> 4);
+                            const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
+                            const uint64_t dwh = descW + (uint64_t)((ws * W_SLOT_BYTES) >> 4);
+                            const uint64_t dwl = dwh + (uint64_t)((bn * 128) >> 4);
+                            if (stacked) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc2, (c | ks) != 0 ? 1u : 0u);
+                                    umma(d_tmem, dal + 2 * ks, dwh + 2 * ks, idesc, 1u);
+                                }
+                            } else {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {   // small terms first
+                                    umma(d_tmem, dal + 2 * ks, dwh + 2 * ks, idesc, (c | ks) != 0 ? 1u : 0u);
+                                    umma(d_tmem, dah + 2 * ks, dwl + 2 * ks, idesc, 1u);
+                                    umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc, 1u);
+                                }
+                            }
+                            umma_commit(&bars.emptyW[ws]);
+                            if (c == nck - 1) umma_commit(&bars.accFull[slot]);
+                        }
+                        __syncwarp();
+                    }
+                    if (dead) break;
                 }
-                if (!dead) {
+                if (pl.n > 0 && !dead) {
                     if (elect_one()) umma_commit(&bars.aFree);
                     __syncwarp();
                     if (lane == 0) BVC_TRACE(7);
@@ -862,7 +906,14 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     if (tid == 128 && j == pl.n - 1) BVC_TRACE(9);
                     tc_fence_after();
                     float v[8];
-                    if (pl.split) {
+                    if (pl.split && (dbg_flags & 2048)) {
+                        // timing probe (wrong results): no tensor-memory read, no reduce-scatter
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                        tc_fence_before();
+                        __syncwarp();
+                        release_acc();
+                    } else if (pl.split) {
                         const int sr = sIt;
                         ++sIt;
                         float acc[32], own[8];
@@ -916,7 +967,9 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         __syncwarp();
                         release_acc();
                     }
-                    finalize8(op, fr, t, m, row, m_tile, col0, v, pf);
+                    finalize8(op, fr, t, m, row, m_tile, col0, v, pf,
+                              (trace && t < trace_frames && tid == 128 && j == pl.n - 1 && (dbg_flags & 64))
+                                  ? trace + (((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS : nullptr);
                 }
                 // ---- end of phase: publish this CTA's outputs to the m-tile's barrier domain ----
                 if (tid == 128) BVC_TRACE(12);
@@ -925,9 +978,6 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                 // acquire, before the bulk copies.  A writer-side fence.proxy.async here would be a MEMBAR.ALL.GPU in each of
                 // the epilogue threads on the critical path of every phase.
                 if (dbg_flags & 32) fence_proxy_async_all();
-                // experiment (debug flag 512): every epilogue thread fences its own stores (in parallel, right behind them)
-                // and the leader's arrival is relaxed, instead of one release-scoped arrival behind the CTA barrier
-                if (dbg_flags & 512) asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
                 {   // barrier over the 8 epilogue warps; a failed wait anywhere retires all of them together
                     uint32_t any;
                     asm volatile(
@@ -957,8 +1007,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             }
                         }
                     }
-                    if (dbg_flags & 512) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
-                    else asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
                     BVC_TRACE(13);
                 }
             }

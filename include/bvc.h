@@ -98,7 +98,7 @@ int bvc_destroy(bvc_handle* h);
 
 /* bvrnn_codec_model.py:38,41 -- strict load of the 'vrnn' state dict (39 tensors,
  * schema SURVEY.md 3.1).  Unknown, missing or mis-shaped tensors fail with
- * BVC_ERR_SCHEMA.  prior.* and log_sigma are accepted and unused. */
+ * BVC_ERR_SCHEMA.  prior.* feeds bvc_encode_ex's prior output; log_sigma is accepted and unused. */
 int bvc_load_bvrnn(bvc_handle* h, const bvc_tensor* tensors, int32_t n);
 
 /* bvrnn_codec_model.py:39,42 -- strict load of the 'generator' state dict
@@ -139,11 +139,44 @@ int bvc_encode_mel(bvc_handle* h, const float* mel_dev, const float* bits_dev, f
                    float* codes_dev, uint64_t* packed_dev, float* logits_dev,
                    float* all_h_dev, float* h_final_dev, float* mel_hat_dev, void* stream);
 
+/* ABI 3: bvc_encode_mel plus the two remaining pieces of the reference's BVRNN.forward (bvrnn.py:86-160):
+ *   uniforms_dev [B,T,z_dim] or NULL   sampled bits z = round(u - 0.5 + p) with caller-supplied uniforms u (bvrnn.py:123-126;
+ *                                      the reference draws u with torch.rand_like) instead of the greedy round(p)
+ *   prior_dev    [B,T,z_dim] or NULL   Bernoulli probabilities of the `prior` head, prior(h_t) (bvrnn.py:68-73,115-120), for
+ *                                      entropy / KL estimates (bvrnn.py:148-158 against sigmoid(logits_dev))
+ * Encoder and decoder state stay in lock-step as in BVRNN.encode (the reference's forward with p_use_gen = 1). */
+int bvc_encode_ex(bvc_handle* h, const float* mel_dev, const float* bits_dev, float bits_scalar,
+                  const float* h0_dev, const float* uniforms_dev, int32_t B, int32_t T,
+                  float* codes_dev, uint64_t* packed_dev, float* logits_dev,
+                  float* all_h_dev, float* h_final_dev, float* mel_hat_dev, float* prior_dev, void* stream);
+
 /* Wire format (new; the reference only has the float layout): one uint64 per frame, bit i = code i, masked bits 0.
  * bvc_encode fills packed_dev; this expands it back to the reference's float codes ({0,1}, 0.5 for bits >= budget,
  * bvrnn.py:191-196) so that bvc_decode_mel can consume it.  bits_dev [B,T] or NULL -> bits_scalar. */
 int bvc_unpack_codes(bvc_handle* h, const uint64_t* packed_dev, const float* bits_dev, float bits_scalar,
                      int32_t B, int32_t T, float* codes_dev, void* stream);
+
+/* ABI 3: BVRNN.decode (bvrnn.py:211-229) straight from the wire words: packed_dev [B,T] uint64 + the bit budgets (bits_dev
+ * [B,T] or NULL -> bits_scalar; ignored by a fixed-rate model).  The {0, 1, 0.5} code vector is formed directly as the
+ * operand of phi_z.0; the float code tensor of the reference (bvrnn.py:191-196, 256 bytes per frame) is never materialised.
+ * Same result as bvc_unpack_codes + bvc_decode_mel. */
+int bvc_decode_packed(bvc_handle* h, const uint64_t* packed_dev, const float* bits_dev, float bits_scalar,
+                      const float* h0_dev, int32_t B, int32_t T, float* mel_dev, float* h_final_dev, void* stream);
+
+/* ABI 3: n-bit-per-frame bit-stream (new).  Per utterance, little-endian:
+ *    0 "BVC1"   4 uint16 z_dim   6 uint8 mode (0: n bits in every frame, 1: per-frame budgets)   7 uint8 n (mode 0)
+ *    8 uint32 T   12 uint32 payload bits   16 [mode 1: T budget bytes, padded to 4]   then the payload: the n_t ACTIVE
+ *    bits of frame 0, 1, ... back to back, LSB first, in 32-bit words.
+ * 3 kbps = 35 bits per frame -> 4.4 bytes per frame on the wire (the word format: 8, the reference's floats: 256).
+ * bvc_bitstream_bytes: size of one utterance's stream (upper bound for mode 1), a valid `stride`.
+ * bvc_pack_bitstream:   packed_dev [B,T] words (+ budgets as for bvc_encode) -> out_dev [B][stride] bytes.
+ * bvc_unpack_bitstream: in_dev [B][stride] -> packed_dev [B,T] words and (nullable) bits_out_dev [B,T] budgets as floats,
+ *                       ready for bvc_decode_packed / bvc_unpack_codes.  T must be the header's T. */
+size_t bvc_bitstream_bytes(const bvc_handle* h, int32_t T, int32_t per_frame_budgets);
+int bvc_pack_bitstream(bvc_handle* h, const uint64_t* packed_dev, const float* bits_dev, float bits_scalar,
+                       int32_t B, int32_t T, uint8_t* out_dev, size_t stride, void* stream);
+int bvc_unpack_bitstream(bvc_handle* h, const uint8_t* in_dev, size_t stride, int32_t B, int32_t T,
+                         uint64_t* packed_dev, float* bits_out_dev, void* stream);
 
 /* bvrnn.py:211-229 (BVRNN.decode).  codes_dev [B,T,z_dim] arbitrary floats. */
 int bvc_decode_mel(bvc_handle* h, const float* codes_dev, const float* h0_dev,

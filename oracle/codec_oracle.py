@@ -106,11 +106,14 @@ def _gru_cell(sd, xin, h):
     return (1.0 - z) * n + z * h
 
 
-def bvrnn_encode(sd, y, bits, h0, var_bit, want_taps=False):
+def bvrnn_encode(sd, y, bits, h0, var_bit, want_taps=False, uniforms=None):
     """y [B,T,80], bits [B,T] (bits per frame), h0 [B,H].
 
     Returns codes [B,T,Z] in {0,1,0.5}, all_h [B,T,H] (state entering frame t),
     final h [B,H], and (optionally) pre-sigmoid logits [B,T,Z].
+    uniforms [B,T,Z] (optional): sampled bits z = round(u - 0.5 + p) instead of round(p)
+    (reference bvrnn.py:123-126 with the uniforms supplied by the caller; encoder and decoder state stay in lock-step
+    exactly as in BVRNN.encode, i.e. the reference's forward with p_use_gen = 1).
     """
     B, T, _ = y.shape
     Z = sd["enc.4.weight"].shape[0]
@@ -125,7 +128,10 @@ def bvrnn_encode(sd, y, bits, h0, var_bit, want_taps=False):
         e = F.elu(F.linear(u, sd["enc.0.weight"], sd["enc.0.bias"]))
         e = F.elu(F.linear(e, sd["enc.2.weight"], sd["enc.2.bias"]))
         logit = F.linear(e, sd["enc.4.weight"], sd["enc.4.bias"])
-        z = torch.round(torch.sigmoid(logit))                        # :191 (round half to even)
+        if uniforms is None:
+            z = torch.round(torch.sigmoid(logit))                    # :191 (round half to even)
+        else:
+            z = torch.round(uniforms[:, t] - 0.5 + torch.sigmoid(logit))   # :126
         if var_bit:                                                  # :193-194
             m = (bits[:, t, None] > bit_idx[None, :]).float()
             z = z * m + 0.5 * (1.0 - m)
@@ -141,6 +147,23 @@ def bvrnn_encode(sd, y, bits, h0, var_bit, want_taps=False):
     if want_taps:
         out = out + (torch.stack(logits, 1),)
     return out
+
+
+def bvrnn_prior(sd, all_h):
+    """prior(h_t) for every frame: all_h [B,T,H] (state entering frame t) -> Bernoulli probabilities [B,T,Z]
+    (reference bvrnn.py:68-73, evaluated at :115-120)."""
+    return torch.sigmoid(_mlp(sd, "prior", (0, 2, 4), all_h, last_act=False))
+
+
+def bvrnn_kld(enc_p, prior_p, bits, var_bit):
+    """KL(enc || prior) per the reference's training forward (bvrnn.py:148-158): per-frame sum over the active bits, mean
+    over the batch, then mean over frames.  enc_p / prior_p [B,T,Z] probabilities, bits [B,T]."""
+    e = enc_p * (torch.log(torch.clip(enc_p, 1e-3)) - torch.log(torch.clip(prior_p, 1e-3))) + \
+        (1 - enc_p) * (torch.log(torch.clip(1 - enc_p, 1e-3)) - torch.log(torch.clip(1 - prior_p, 1e-3)))
+    if var_bit:
+        mask = (bits[:, :, None] > torch.arange(enc_p.shape[-1], device=enc_p.device)[None, None, :]).float()
+        e = e * mask
+    return e.sum(-1).mean(0).mean()
 
 
 def bvrnn_decode(sd, z, h0):

@@ -18,6 +18,7 @@ Fixtures (all float32 unless noted):
   synth_var_aa_small.npz  configs/config_varBitRate_antialias.toml (anti-aliased activations in every stage and
                         before conv_post; checkpoint with the Activation1d schema): codes, dec_mel, wav
   aa_filter.npz         the reference's 12-tap Kaiser-sinc filter (alias_free_torch/filter.py:28-59), pins synth.py's
+  synth_var_stochastic.npz  sampled bits with supplied uniforms + prior head + KL (`python -m oracle.gen_golden stochastic`)
   stim01_var.npz        BASELINE config #1 input (MUSHRA stim_01 ref.wav, CC BY 4.0,
                         resampled 24k->22.05k, peak-normalised) at 3000 bps
 """
@@ -76,7 +77,54 @@ def save(name, d, **extra):
     print("wrote", name, {k: getattr(v, "shape", v) for k, v in out.items()})
 
 
+def gen_stochastic():
+    """synth_var_stochastic.npz: the reference's sampled-bit path (bvrnn.py:86-160 with p_use_gen = 1, greedy = False), i.e.
+    z = round(u - 0.5 + p) with the uniforms u supplied by us (torch.rand_like is patched for the duration of the call to hand
+    out the fixture's uniforms frame by frame), per-frame bit budgets, the `prior` head and the KL term.  Taps by hooks:
+    z_t = input of phi_z, p_t = output of enc, prior_t = output of prior."""
+    ref = ref_shim.import_reference()
+    p_b, p_v = write_synthetic_checkpoints(CKPT_DIR, seed=SEED, sharpen=SHARPEN)
+    cfg_var = os.path.join(ROOT, "configs", "config_varBitRate.toml")
+    m = ref.BVRNNCodecModel(cfg_var, p_b, p_v).eval()
+    x = synth_audio(2, 4000 + 33, seed=21)
+    g = torch.Generator().manual_seed(99)
+    with torch.no_grad():
+        mel = ref.mel_spectrogram(x * ref.SCALING, n_fft=1024, num_mels=80, sampling_rate=22050, hop_size=256,
+                                  win_size=1024, fmin=0, fmax=8000, padding_left=256).permute(0, 2, 1).contiguous()
+        B, T, _ = mel.shape
+        u = torch.rand(B, T, 64, generator=g)
+        bits = torch.randint(0, 66, (B, T), generator=g).float()
+        taps = {"z": [], "p": [], "prior": []}
+        hooks = [m.bvrnn.phi_z.register_forward_pre_hook(lambda mod, inp: taps["z"].append(inp[0].detach().clone())),
+                 m.bvrnn.enc.register_forward_hook(lambda mod, i, o: taps["p"].append(o.detach().clone())),
+                 m.bvrnn.prior.register_forward_hook(lambda mod, i, o: taps["prior"].append(o.detach().clone()))]
+        frame = {"t": 0}
+        orig = torch.rand_like
+
+        def fake_rand_like(t, *a, **k):
+            out = u[:, frame["t"]].to(t.dtype)
+            frame["t"] += 1
+            assert out.shape == t.shape
+            return out
+
+        torch.rand_like = fake_rand_like
+        try:
+            m.bvrnn.device = torch.device("cpu")
+            dec, kld = m.bvrnn(mel, 1.0, False, bits)
+        finally:
+            torch.rand_like = orig
+            for h in hooks:
+                h.remove()
+    assert frame["t"] == T
+    save("synth_var_stochastic.npz",
+         dict(x=x, mel=mel, uniforms=u, bits=bits, codes=torch.stack(taps["z"], 1), enc_p=torch.stack(taps["p"], 1),
+              prior_p=torch.stack(taps["prior"], 1), dec_mel=dec, kld=kld.reshape(1)), ckpt_seed=SEED, ckpt_sharpen=SHARPEN)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "stochastic":
+        gen_stochastic()
+        return
     torch.manual_seed(0)
     ref = ref_shim.import_reference()
     os.makedirs(GOLD, exist_ok=True)

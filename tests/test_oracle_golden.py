@@ -80,3 +80,23 @@ def test_reference_cross_check_when_available(ckpts, cfg_var):
     oc = o.encode(x, 1500)
     assert torch.equal(rc, oc)
     assert (o.decode(oc, x.shape[1]) - rw).abs().max() < 2e-5
+
+
+def test_oracle_stochastic_mode_and_prior_match_reference(oracle_var):
+    """Sampled bits z = round(u - 0.5 + p) with supplied uniforms, per-frame budgets, the prior head and the KL term against
+    the unmodified reference's training forward (p_use_gen = 1, greedy = False; torch.rand_like patched to our uniforms)."""
+    from oracle.codec_oracle import bvrnn_decode, bvrnn_encode, bvrnn_kld, bvrnn_prior
+    g = golden("synth_var_stochastic.npz")
+    mel, u, bits = (torch.from_numpy(g[k]) for k in ("mel", "uniforms", "bits"))
+    with torch.no_grad():
+        codes, all_h, _, logits = bvrnn_encode(oracle_var.sd, mel, bits, torch.zeros(2, 1024), True, want_taps=True, uniforms=u)
+        assert np.array_equal(codes.numpy(), g["codes"])                              # bit-exact, masks included
+        p = torch.sigmoid(logits)
+        assert np.abs(p.numpy() - g["enc_p"]).max() < 2e-6
+        prior = bvrnn_prior(oracle_var.sd, all_h)
+        assert np.abs(prior.numpy() - g["prior_p"]).max() < 2e-6
+        assert abs(float(bvrnn_kld(p, prior, bits, True)) - float(g["kld"][0])) < 1e-4
+        dec, _ = bvrnn_decode(oracle_var.sd, codes, torch.zeros(2, 1024))
+        assert np.abs(dec.numpy() - g["dec_mel"]).max() < 5e-6
+        greedy = bvrnn_encode(oracle_var.sd, mel, bits, torch.zeros(2, 1024), True)[0]
+        assert not np.array_equal(greedy.numpy(), g["codes"])                         # the uniforms matter

@@ -20,9 +20,8 @@ d[d == 0] = np.nan
 fr = d[:, frame]
 if CLK:
     ev = [("Aiss", 3), ("c0", 16), ("c1", 17), ("c2", 18), ("c3", 19),
-          ("A0", 24), ("W0", 25), ("I0", 26), ("A1", 27), ("W1", 28), ("I1", 29), ("A2", 30), ("W2", 31), ("I2", 32),
-          ("A3", 33), ("W3", 34), ("I3", 35), ("mmaIss", 7), ("acc0", 8), ("accL", 9), ("tmem", 10), ("stores", 0), ("sent", 11),
-          ("recv", 14), ("sum", 15), ("freed", 1), ("fin", 12), ("barred", 36), ("arr", 13)]
+          ("mmaIss", 7), ("acc0", 8), ("accL", 9), ("tmem", 10), ("stores", 0), ("sent", 11),
+          ("recv", 14), ("sum", 15), ("freed", 1), ("f.add", 20), ("f.elu", 21), ("f.img", 22), ("f.out", 23), ("fin", 12), ("barred", 36), ("arr", 13)]
     print("frame %d: %d CTAs; clk after the CTA's own phase-barrier pass (median / max over busy CTAs)" % (frame, n_cta))
     print("phase busy | " + " ".join("%6s" % n for n, _ in ev))
     for ph in range(n_ph):
