@@ -51,6 +51,11 @@ SYMBOLS = {
     "bvc_bitstream_bytes": (C.c_size_t, [_P, _I, _I]),
     "bvc_pack_bitstream": (C.c_int, [_P, _P, _P, _F, _I, _I, _P, C.c_size_t, _P]),
     "bvc_unpack_bitstream": (C.c_int, [_P, _P, C.c_size_t, _I, _I, _P, _P, _P]),
+    "bvc_stream_create": (C.c_int, [_P, _I, C.POINTER(_P)]),
+    "bvc_stream_destroy": (C.c_int, [_P]),
+    "bvc_stream_reset": (C.c_int, [_P, _P, _P]),
+    "bvc_stream_encode_step": (C.c_int, [_P, _P, _P, _P, _F, _F, _P, _P, _P]),
+    "bvc_stream_decode_step": (C.c_int, [_P, _P, _P, _P, _F, _F, _P, _P]),
     "bvc_vocode": (C.c_int, [_P, _P, _I, _I, _I, _F, _P, _P]),
     "bvc_vocoder_out_len": (C.c_int64, [_P, _I]),
     "bvc_encode_host": (C.c_int, [_P, _P, _I, _I, _F, _F, _P]),

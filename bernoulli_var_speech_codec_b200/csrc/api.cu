@@ -3,6 +3,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -1046,6 +1047,135 @@ int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T
     if (rc || rc2) return rc ? rc : rc2;
     BVC_CUDA(cudaStreamSynchronize(s));
     return rec_poll_aborts(h->bw.rw, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming sessions
+// ---------------------------------------------------------------------------------------------
+struct bvc_stream {
+    bvc_handle* h = nullptr;
+    int S = 0;
+    float *fifo = nullptr, *h_enc = nullptr, *h_dec = nullptr, *voc = nullptr;   // per-stream state
+    int* n_samples = nullptr;
+    float *win = nullptr, *mel = nullptr, *codes = nullptr, *h_tmp = nullptr, *dmel = nullptr;   // per-hop scratch
+    unsigned long long* words = nullptr;
+    unsigned char* valid = nullptr;
+    size_t voc_floats = 0;
+    std::vector<void*> allocs;
+};
+
+int bvc_stream_create(bvc_handle* h, int32_t n_streams, bvc_stream** out) {
+    REQUIRE(h && out && n_streams > 0, BVC_ERR_INVALID, "bvc_stream_create: bad argument");
+    REQUIRE(h->have_bvrnn && h->have_voc && h->have_frontend, BVC_ERR_STATE, "bvc_stream_create: weights / front-end not loaded");
+    REQUIRE(h->bw.Z == 64 && h->bw.rw.ready, BVC_ERR_INVALID, "bvc_stream_create: needs z_dim = 64 and the persistent-kernel weights");
+    *out = nullptr;
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    bvc_stream* st = new bvc_stream();
+    st->h = h;
+    st->S = n_streams;
+    const size_t S = (size_t)n_streams, H = h->bw.H, X = h->bw.X, Z = h->bw.Z, N = h->cfg.n_fft;
+    st->voc_floats = vocoder_stream_state_floats(h->vw, n_streams);
+    bool ok = true;
+    auto alloc = [&](size_t bytes) -> void* {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); ok = false; return nullptr; }
+        st->allocs.push_back(p);
+        return p;
+    };
+    st->fifo = (float*)alloc(S * N * 4);        st->h_enc = (float*)alloc(S * H * 4);   st->h_dec = (float*)alloc(S * H * 4);
+    st->voc = (float*)alloc(st->voc_floats * 4); st->n_samples = (int*)alloc(S * 4);
+    st->win = (float*)alloc(S * N * 4);         st->mel = (float*)alloc(S * X * 4);     st->codes = (float*)alloc(S * Z * 4);
+    st->h_tmp = (float*)alloc(S * H * 4);       st->dmel = (float*)alloc(S * X * 4);
+    st->words = (unsigned long long*)alloc(S * 8); st->valid = (unsigned char*)alloc(S);
+    if (!ok) {
+        for (void* p : st->allocs) cudaFree(p);
+        delete st;
+        set_error("bvc_stream_create: device allocation failed");
+        return BVC_ERR_NOMEM;
+    }
+    *out = st;
+    return bvc_stream_reset(st, nullptr, nullptr);
+}
+
+int bvc_stream_destroy(bvc_stream* st) {
+    if (!st) return BVC_OK;
+    Guard g(st->h);
+    cudaDeviceSynchronize();
+    for (void* p : st->allocs) cudaFree(p);
+    delete st;
+    return BVC_OK;
+}
+
+int bvc_stream_reset(bvc_stream* st, const uint8_t* which_dev, void* stream) {
+    REQUIRE(st, BVC_ERR_INVALID, "bvc_stream_reset: null session");
+    bvc_handle* h = st->h;
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int S = st->S;
+    int rc;
+    if ((rc = stream_reset_rows(st->fifo, which_dev, S, h->cfg.n_fft, s))) return rc;
+    if ((rc = stream_reset_rows(st->h_enc, which_dev, S, h->bw.H, s))) return rc;
+    if ((rc = stream_reset_rows(st->h_dec, which_dev, S, h->bw.H, s))) return rc;
+    if ((rc = stream_reset_ints(st->n_samples, which_dev, S, s))) return rc;
+    if ((rc = vocoder_stream_reset(h->vw, st->voc, which_dev, S, s))) return rc;
+    return BVC_OK;
+}
+
+int bvc_stream_encode_step(bvc_stream* st, const float* x_new_dev, const uint8_t* active_dev, const float* bits_dev,
+                           float bits_scalar, float scale, uint64_t* packed_out_dev, uint8_t* valid_out_dev, void* stream) {
+    REQUIRE(st && x_new_dev && packed_out_dev, BVC_ERR_INVALID, "bvc_stream_encode_step: null argument");
+    bvc_handle* h = st->h;
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int S = st->S;
+    int rc = rec_poll_aborts(h->bw.rw, false);
+    if (rc) return rc;
+    if ((rc = ensure_workspace(h, bvrnn_workspace_floats(h->bw, S, 1)))) return rc;
+    if ((rc = ws_acquire(h, s))) return rc;
+    rc = [&]() -> int {
+        int r = stream_push(st->fifo, st->n_samples, x_new_dev, active_dev, S, h->cfg.hop, h->cfg.n_fft, h->cfg.pad_left, st->win,
+                            st->valid, s);
+        if (r) return r;
+        // one frame per stream, already framed: L = hop = n_fft and pad_left = 0 make the front end take each row as one frame
+        if ((r = logmel_forward(h->ft, st->win, S, h->cfg.n_fft, h->cfg.n_fft, 0, scale, st->mel, s))) return r;
+        if ((r = bvrnn_encode(h->bw, h->ws, st->mel, bits_dev, bits_scalar, st->h_enc, S, 1, st->codes, st->words, nullptr, nullptr,
+                              st->h_tmp, nullptr, h->precision, s)))
+            return r;
+        if ((r = stream_commit(st->h_enc, st->h_tmp, st->valid, S, h->bw.H, s))) return r;
+        if ((r = stream_mask_words((unsigned long long*)packed_out_dev, st->words, st->valid, S, s))) return r;
+        if (valid_out_dev) BVC_CUDA(cudaMemcpyAsync(valid_out_dev, st->valid, S, cudaMemcpyDeviceToDevice, s));
+        return BVC_OK;
+    }();
+    const int rc2 = ws_release(h, s);
+    return rc ? rc : rc2;
+}
+
+int bvc_stream_decode_step(bvc_stream* st, const uint64_t* packed_dev, const uint8_t* valid_dev, const float* bits_dev,
+                           float bits_scalar, float inv_scale_div, float* wav_out_dev, void* stream) {
+    REQUIRE(st && packed_dev && wav_out_dev, BVC_ERR_INVALID, "bvc_stream_decode_step: null argument");
+    bvc_handle* h = st->h;
+    Guard g(h);
+    if (!g.ok) return BVC_ERR_DEVICE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int S = st->S;
+    int rc = rec_poll_aborts(h->bw.rw, false);
+    if (rc) return rc;
+    const size_t need = std::max(bvrnn_workspace_floats(h->bw, S, 1), vocoder_stream_workspace_floats(h->vw, S));
+    if ((rc = ensure_workspace(h, need))) return rc;
+    if ((rc = ws_acquire(h, s))) return rc;
+    rc = [&]() -> int {
+        int r = bvrnn_decode(h->bw, h->ws, nullptr, st->h_dec, S, 1, st->dmel, st->h_tmp, h->precision, s,
+                             (const unsigned long long*)packed_dev, bits_dev, bits_scalar);
+        if (r) return r;
+        if ((r = stream_commit(st->h_dec, st->h_tmp, valid_dev, S, h->bw.H, s))) return r;
+        h->ws.used = 0;
+        return vocoder_stream_step(h->vw, h->ws, st->voc, st->dmel, S, valid_dev, inv_scale_div, wav_out_dev, h->precision, s);
+    }();
+    const int rc2 = ws_release(h, s);
+    return rc ? rc : rc2;
 }
 
 float bvc_last_recurrent_ms(const bvc_handle* h) {

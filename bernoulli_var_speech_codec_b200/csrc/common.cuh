@@ -271,6 +271,21 @@ size_t vocoder_workspace_floats(const VocoderWeights& w, int B, int T);
 int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, const float* mel, int B, int T,
                     int length, float inv_scale_div, float* wav, int precision, cudaStream_t stream);
 
+// hop-by-hop vocoder of the streaming sessions (vocoder.cu): per-stream stage-input rings in `state`
+size_t vocoder_stream_state_floats(const VocoderWeights& w, int S);
+size_t vocoder_stream_workspace_floats(const VocoderWeights& w, int S);
+int vocoder_stream_reset(const VocoderWeights& w, float* state, const unsigned char* which, int S, cudaStream_t stream);
+int vocoder_stream_step(const VocoderWeights& w, Workspace& ws, float* state, const float* mel_new, int S,
+                        const unsigned char* active, float inv_scale_div, float* wav_out, int precision, cudaStream_t stream);
+
+// streaming session kernels (stream.cu)
+int stream_push(float* fifo, int* n_samples, const float* x_new, const unsigned char* active, int S, int hop, int n_fft,
+                int pad_left, float* win, unsigned char* valid, cudaStream_t s);
+int stream_commit(float* dst, const float* src, const unsigned char* mask, int S, int n, cudaStream_t s);
+int stream_mask_words(unsigned long long* out, const unsigned long long* in, const unsigned char* mask, int S, cudaStream_t s);
+int stream_reset_rows(float* p, const unsigned char* which, int S, size_t n, cudaStream_t s);
+int stream_reset_ints(int* p, const unsigned char* which, int S, cudaStream_t s);
+
 // ---------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------

@@ -1605,6 +1605,140 @@ static void vocoder_dims(const VocoderWeights& w, int T, int64_t* n, int* C) {
     }
 }
 
+struct StageIn {            // input of a stage's transposed convolution: n_parts channel-last tensors [B, n_in, C_in] (their mean)
+    const float* p[3];
+    int n_parts;
+    long long bstride;      // floats per sequence
+    int n_in;
+};
+struct PostFuse {           // tail fused into the last launch of stage 3 (SnakeBeta -> conv_post -> tanh -> / scale -> [:length])
+    bool enable;
+    float inv_scale_div;
+    float* wav;
+    int length;
+};
+
+// Stage i without anti-aliasing: ConvTranspose1d + the three resblocks on B sequences of in.n_in input rows -> out[0..2]
+// ([B, n_out, C] channel-last partial tensors, or one mean tensor in out[0] when *single), n_out = U (n_in + 1).
+// Shared by the offline vocoder_forward and the hop-by-hop vocoder_stream_step (which feeds it short "virtual utterances").
+static int run_plain_stage(const VocoderWeights& w, int i, const StageIn& in, int n_out, float* x0, float* const out[3], int B,
+                           int precision, const PostFuse& pf, bool* single, bool* post_done, cudaStream_t stream) {
+    static const int kTT[4] = {128, 256, 256, 512};
+    static const int umma_mask = getenv("BVC_VOC_UMMA") ? atoi(getenv("BVC_VOC_UMMA")) : 0x7;
+    const int Cs = w.c0 >> (i + 1);
+    *single = false;
+    auto run_upsample = [&]() -> int {
+        UpsampleArgs up;
+        up.n_parts = in.n_parts;
+        for (int q = 0; q < 3; ++q) up.in_p[q] = in.p[q];
+        up.in_bstride = in.bstride;
+        up.n_in = in.n_in;
+        up.n_out = n_out;
+        up.b_up = w.b_up[i];
+        up.upf_h = w.upf_h[i];
+        up.upf_l = w.upf_l[i];
+        up.x0 = x0;
+        switch (Cs) {
+            case 64: return launch_upsample<64, 8>(up, B, stream);
+            case 32: return launch_upsample<32, 8>(up, B, stream);
+            case 16: return launch_upsample<16, 2>(up, B, stream);
+            default: return launch_upsample<8, 2>(up, B, stream);
+        }
+    };
+        if (precision >= 1 && ((umma_mask >> i) & 1) && w.umma[i].ready) {
+            // tcgen05 stage kernel: C <= 32: all three resblocks per CTA, the output is their mean; C = 64: one resblock per CTA
+            const bool all_chains = Cs <= 32;
+            { const int rc_up = run_upsample(); if (rc_up != BVC_OK) return rc_up; }
+            int rc;
+            UmmaStageArgs ua;
+            ua.x0 = x0;
+            ua.n_out = n_out;
+            for (int cc = 0; cc < 3; ++cc) {
+                const AmpBlockWeights& bw = w.blocks[i * 3 + (2 - cc)];
+                for (int q = 0; q < 6; ++q) { ua.ea[cc][q] = bw.act[q].ea; ua.ieb[cc][q] = bw.act[q].inv_eb; }
+                ua.out[cc] = all_chains ? out[0] : out[2 - cc];     // chain cc = resblock kernel index 2 - cc
+            }
+            ua.w = w.umma[i];
+            ua.trace = nullptr;
+            static unsigned long long* trace_dev = nullptr;
+            const bool tracing = getenv("BVC_VOC_TRACE") && atoi(getenv("BVC_VOC_TRACE")) == i;
+            if (tracing) {
+                if (!trace_dev) BVC_CUDA(cudaMalloc(&trace_dev, 80 * sizeof(unsigned long long)));
+                BVC_CUDA(cudaMemsetAsync(trace_dev, 0, 80 * sizeof(unsigned long long), stream));
+                ua.trace = trace_dev;
+            }
+            switch (Cs) {
+                case 64: rc = launch_stage_umma<64, 8, 1, 1>(ua, B, stream); break;
+                case 32: rc = launch_stage_umma<32, 8, 1, 3>(ua, B, stream); break;
+                case 16: rc = launch_stage_umma<16, 2, 2, 3>(ua, B, stream); break;
+                default: rc = launch_stage_umma<8, 2, 2, 3>(ua, B, stream); break;
+            }
+            if (rc != BVC_OK) return rc;
+            if (tracing) {   // per job: MMA warp got the operand / issued all MMAs, epilogue saw the result / finished
+                unsigned long long hbuf[80];
+                BVC_CUDA(cudaStreamSynchronize(stream));
+                BVC_CUDA(cudaMemcpy(hbuf, trace_dev, sizeof(hbuf), cudaMemcpyDeviceToHost));
+                const unsigned long long z = hbuf[72];
+                fprintf(stderr, "stage %d tile trace (us): prologue %.2f\n", i, (hbuf[73] - z) / 1e3);
+                for (int ji = 0; ji < 18; ++ji)
+                    if (hbuf[ji * 4])
+                        fprintf(stderr, "  job %2d chain %d layer %d conv%d steps %2d: mma_start %6.2f mma_issued %6.2f epi_start %6.2f epi_done %6.2f\n", ji,
+                                ua.w.jobs[ji].chain, ua.w.jobs[ji].layer, ua.w.jobs[ji].conv2 + 1, ua.w.jobs[ji].steps, (hbuf[ji * 4] - z) / 1e3,
+                                (hbuf[ji * 4 + 1] - z) / 1e3, (hbuf[ji * 4 + 2] - z) / 1e3, (hbuf[ji * 4 + 3] - z) / 1e3);
+            }
+            if (all_chains) *single = true;
+            return BVC_OK;
+        }
+        for (int jj = 0; jj < 3; ++jj) {
+            const int j = 2 - jj;   // largest kernel first
+            const AmpBlockWeights& bw = w.blocks[i * 3 + j];
+            StageArgs a;
+            a.n_parts = in.n_parts;
+            for (int q = 0; q < 3; ++q) a.in_p[q] = in.p[q];
+            a.in_bstride = in.bstride;
+            a.n_in = in.n_in;
+            a.n_out = n_out;
+            a.w_up = w.w_up[i];
+            a.b_up = w.b_up[i];
+            a.upf_h = w.upf_h[i];
+            a.upf_l = w.upf_l[i];
+            for (int l = 0; l < 3; ++l) {
+                a.w1[l] = bw.w1[l]; a.b1[l] = bw.b1[l];
+                a.w2[l] = bw.w2[l]; a.b2[l] = bw.b2[l];
+                a.f1h[l] = bw.f1h[l]; a.f1l[l] = bw.f1l[l];
+                a.f2h[l] = bw.f2h[l]; a.f2l[l] = bw.f2l[l];
+                a.dil[l] = w.dil[l];
+            }
+            for (int q = 0; q < 6; ++q) { a.ea[q] = bw.act[q].ea; a.ieb[q] = bw.act[q].inv_eb; }
+            a.out = out[j];
+            a.TT = kTT[i];
+            a.wav = nullptr;
+            if (i == 3 && j == 0 && precision >= 1 && !w.antialias_post && pf.enable) {
+                // last launch of the vocoder: the k = 3 resblock kernel of the last stage also does the tail
+                // (mean with the k = 7 and k = 11 partials -> SnakeBeta -> conv_post -> tanh), post_kernel is skipped
+                a.post_p1 = out[1];
+                a.post_p2 = out[2];
+                a.post_ea = w.act_post.ea;
+                a.post_ieb = w.act_post.inv_eb;
+                a.post_w = w.w_post;
+                a.post_bias = w.b_post;
+                a.post_inv_scale_div = pf.inv_scale_div;
+                a.wav = pf.wav;
+                a.n_wav = pf.length < n_out ? pf.length : n_out;
+                *post_done = a.n_wav > 0;
+            }
+            int rc;
+            switch (i) {
+                case 0: rc = launch_stage_k<64, 8>(bw.k, a, B, precision, stream); break;
+                case 1: rc = launch_stage_k<32, 8>(bw.k, a, B, precision, stream); break;
+                case 2: rc = launch_stage_k<16, 2>(bw.k, a, B, precision, stream); break;
+                default: rc = launch_stage_k<8, 2>(bw.k, a, B, precision, stream); break;
+            }
+            if (rc != BVC_OK) return rc;
+        }
+    return BVC_OK;
+}
+
 size_t vocoder_workspace_floats(const VocoderWeights& w, int B, int T) {
     int64_t n[5];
     int C[5];
@@ -1728,105 +1862,27 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
             }
             continue;
         }
-        if (precision >= 1 && ((umma_mask >> i) & 1) && w.umma[i].ready) {
-            // tcgen05 stage kernel: C <= 32: all three resblocks per CTA, the output is their mean; C = 64: one resblock per CTA
-            const bool all_chains = vb.C[i + 1] <= 32;
-            { const int rc_up = run_upsample(i); if (rc_up != BVC_OK) return rc_up; }
-            int rc;
-            UmmaStageArgs ua;
-            ua.x0 = vb.x0;
-            ua.n_out = (int)vb.n[i + 1];
-            for (int cc = 0; cc < 3; ++cc) {
-                const AmpBlockWeights& bw = w.blocks[i * 3 + (2 - cc)];
-                for (int q = 0; q < 6; ++q) { ua.ea[cc][q] = bw.act[q].ea; ua.ieb[cc][q] = bw.act[q].inv_eb; }
-                ua.out[cc] = all_chains ? vb.part[i][0] : vb.part[i][2 - cc];     // chain cc = resblock kernel index 2 - cc
-            }
-            ua.w = w.umma[i];
-            ua.trace = nullptr;
-            static unsigned long long* trace_dev = nullptr;
-            const bool tracing = getenv("BVC_VOC_TRACE") && atoi(getenv("BVC_VOC_TRACE")) == i;
-            if (tracing) {
-                if (!trace_dev) BVC_CUDA(cudaMalloc(&trace_dev, 80 * sizeof(unsigned long long)));
-                BVC_CUDA(cudaMemsetAsync(trace_dev, 0, 80 * sizeof(unsigned long long), stream));
-                ua.trace = trace_dev;
-            }
-            switch (vb.C[i + 1]) {
-                case 64: rc = launch_stage_umma<64, 8, 1, 1>(ua, B, stream); break;
-                case 32: rc = launch_stage_umma<32, 8, 1, 3>(ua, B, stream); break;
-                case 16: rc = launch_stage_umma<16, 2, 2, 3>(ua, B, stream); break;
-                default: rc = launch_stage_umma<8, 2, 2, 3>(ua, B, stream); break;
-            }
-            if (rc != BVC_OK) return rc;
-            if (tracing) {   // per job: MMA warp got the operand / issued all MMAs, epilogue saw the result / finished
-                unsigned long long hbuf[80];
-                BVC_CUDA(cudaStreamSynchronize(stream));
-                BVC_CUDA(cudaMemcpy(hbuf, trace_dev, sizeof(hbuf), cudaMemcpyDeviceToHost));
-                const unsigned long long z = hbuf[72];
-                fprintf(stderr, "stage %d tile trace (us): prologue %.2f\n", i, (hbuf[73] - z) / 1e3);
-                for (int ji = 0; ji < 18; ++ji)
-                    if (hbuf[ji * 4])
-                        fprintf(stderr, "  job %2d chain %d layer %d conv%d steps %2d: mma_start %6.2f mma_issued %6.2f epi_start %6.2f epi_done %6.2f\n", ji,
-                                ua.w.jobs[ji].chain, ua.w.jobs[ji].layer, ua.w.jobs[ji].conv2 + 1, ua.w.jobs[ji].steps, (hbuf[ji * 4] - z) / 1e3,
-                                (hbuf[ji * 4 + 1] - z) / 1e3, (hbuf[ji * 4 + 2] - z) / 1e3, (hbuf[ji * 4 + 3] - z) / 1e3);
-            }
-            if (all_chains) {
-                vb.part[i][1] = vb.part[i][2] = vb.part[i][0];   // parity taps read "three partials": all the same mean
-                single[i] = true;
-            }
-            continue;
-        }
-        for (int jj = 0; jj < 3; ++jj) {
-            const int j = 2 - jj;   // largest kernel first
-            const AmpBlockWeights& bw = w.blocks[i * 3 + j];
-            StageArgs a;
+        {
+            StageIn in;
             if (i == 0) {
-                a.n_parts = 1;
-                a.in_p[0] = a.in_p[1] = a.in_p[2] = vb.pre;
-                a.in_bstride = (long long)(T + 6) * w.c0;
+                in.n_parts = 1;
+                in.p[0] = in.p[1] = in.p[2] = vb.pre;
+                in.bstride = (long long)(T + 6) * w.c0;
             } else {
-                a.n_parts = single[i - 1] ? 1 : 3;
-                for (int q = 0; q < 3; ++q) a.in_p[q] = vb.part[i - 1][single[i - 1] ? 0 : q];
-                a.in_bstride = (long long)vb.n[i] * vb.C[i];
+                in.n_parts = single[i - 1] ? 1 : 3;
+                for (int q = 0; q < 3; ++q) in.p[q] = vb.part[i - 1][single[i - 1] ? 0 : q];
+                in.bstride = (long long)vb.n[i] * vb.C[i];
             }
-            a.n_in = (int)vb.n[i];
-            a.n_out = (int)vb.n[i + 1];
-            a.w_up = w.w_up[i];
-            a.b_up = w.b_up[i];
-            a.upf_h = w.upf_h[i];
-            a.upf_l = w.upf_l[i];
-            for (int l = 0; l < 3; ++l) {
-                a.w1[l] = bw.w1[l]; a.b1[l] = bw.b1[l];
-                a.w2[l] = bw.w2[l]; a.b2[l] = bw.b2[l];
-                a.f1h[l] = bw.f1h[l]; a.f1l[l] = bw.f1l[l];
-                a.f2h[l] = bw.f2h[l]; a.f2l[l] = bw.f2l[l];
-                a.dil[l] = w.dil[l];
-            }
-            for (int q = 0; q < 6; ++q) { a.ea[q] = bw.act[q].ea; a.ieb[q] = bw.act[q].inv_eb; }
-            a.out = vb.part[i][j];
-            a.TT = kTT[i];
-            a.wav = nullptr;
-            if (i == 3 && j == 0 && precision >= 1 && !w.antialias_post && fuse_post) {
-                // last launch of the vocoder: the k = 3 resblock kernel of the last stage also does the tail
-                // (mean with the k = 7 and k = 11 partials -> SnakeBeta -> conv_post -> tanh), post_kernel is skipped
-                a.post_p1 = vb.part[3][1];
-                a.post_p2 = vb.part[3][2];
-                a.post_ea = w.act_post.ea;
-                a.post_ieb = w.act_post.inv_eb;
-                a.post_w = w.w_post;
-                a.post_bias = w.b_post;
-                a.post_inv_scale_div = inv_scale_div;
-                a.wav = wav;
-                a.n_wav = length < (int)vb.n[4] ? length : (int)vb.n[4];
-                post_done = a.n_wav > 0;
-            }
-            int rc;
-            switch (i) {
-                case 0: rc = launch_stage_k<64, 8>(bw.k, a, B, precision, stream); break;
-                case 1: rc = launch_stage_k<32, 8>(bw.k, a, B, precision, stream); break;
-                case 2: rc = launch_stage_k<16, 2>(bw.k, a, B, precision, stream); break;
-                default: rc = launch_stage_k<8, 2>(bw.k, a, B, precision, stream); break;
-            }
+            in.n_in = (int)vb.n[i];
+            PostFuse pf;
+            pf.enable = fuse_post;
+            pf.inv_scale_div = inv_scale_div;
+            pf.wav = wav;
+            pf.length = length;
+            float* outs[3] = {vb.part[i][0], vb.part[i][1], vb.part[i][2]};
+            const int rc = run_plain_stage(w, i, in, (int)vb.n[i + 1], vb.x0, outs, B, precision, pf, &single[i], &post_done, stream);
             if (rc != BVC_OK) return rc;
+            if (single[i]) vb.part[i][1] = vb.part[i][2] = vb.part[i][0];   // parity taps read "three partials": all the same mean
         }
     }
     if (!post_done) {
@@ -1859,6 +1915,177 @@ int vocoder_forward(const VocoderWeights& w, Workspace& ws, VocoderBuffers& vb, 
             BVC_CHECK_LAUNCH();
         }
     }
+    return BVC_OK;
+}
+
+
+// =============================================================================================
+// Hop-by-hop vocoder for the streaming sessions (BASELINE configs[4])
+// =============================================================================================
+// Per stream and stage the session keeps a ring of the stage's INPUT rows (the previous stage's output, before the
+// transposed convolution): H_i history rows + the rows of the new hop.  A hop runs every stage on these short "virtual
+// utterances" with the same kernels as the offline path and keeps only the rows of the new hop:
+//     rows of a stage output that are exact = those whose receptive field (transposed conv: 1 input row back; resblocks:
+//     12 (k - 1) = 120 rows of x0; tail: 6 more rows) lies inside the ring  ->  H = {16, 16, 61, 64} input rows.
+// Work per hop and stream: 2 MMA tiles per stage (the warm-up rows ride in the 128-row tile the new rows need anyway),
+// instead of re-synthesising the last 29 frames (75 tiles) as round 1's chunked decoder did.  Rings start at zero
+// ("zero-state start"): the first 27 frames of a stream differ from the offline decode, which zero-pads every conv input
+// at t < 0 instead (stated edge policy; from frame 27 on the outputs are those of the offline path).
+namespace {
+
+constexpr int kStreamHist[4] = {16, 16, 61, 64};
+
+// one block per stream: ring <- shift left by n_new, append mean(src parts)[src_row0 .. src_row0 + n_new)
+__global__ void __launch_bounds__(256) ring_push_kernel(float* __restrict__ ring, int R, int C, const float* __restrict__ s0,
+                                                        const float* __restrict__ s1, const float* __restrict__ s2, int n_parts,
+                                                        long long src_bstride, int src_row0, int n_new,
+                                                        const unsigned char* __restrict__ active) {
+    extern __shared__ float keep[];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (active && !active[s]) return;
+    float* r = ring + (size_t)s * R * C;
+    const int n_keep = (R - n_new) * C;
+    for (int i = tid; i < n_keep; i += 256) keep[i] = r[(size_t)n_new * C + i];
+    __syncthreads();
+    for (int i = tid; i < n_keep; i += 256) r[i] = keep[i];
+    const size_t so = (size_t)s * src_bstride + (size_t)src_row0 * C;
+    for (int i = tid; i < n_new * C; i += 256) {
+        float v = s0[so + i];
+        if (n_parts == 3) v = ((v + s1[so + i]) + s2[so + i]) / 3.0f;
+        r[n_keep + i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) stream_tail_kernel(const float* __restrict__ wav_v, int n_v, int row0, int n,
+                                                          const unsigned char* __restrict__ active, float* __restrict__ out) {
+    const int s = blockIdx.x;
+    const bool on = !active || active[s];
+    for (int i = threadIdx.x; i < n; i += 256) out[(size_t)s * n + i] = on ? wav_v[(size_t)s * n_v + row0 + i] : 0.f;
+}
+
+}  // namespace
+
+size_t vocoder_stream_state_floats(const VocoderWeights& w, int S) {
+    size_t n = (size_t)S * 7 * w.n_mels;
+    int new_rows = 1;
+    for (int i = 0; i < 4; ++i) {
+        n += (size_t)S * (kStreamHist[i] + new_rows) * (w.c0 >> i) + 64;
+        new_rows *= w.rates[i];
+    }
+    return n + 64;
+}
+
+// zero the rings of the streams marked in `which` (nullptr: all)
+int vocoder_stream_reset(const VocoderWeights& w, float* state, const unsigned char* which, int S, cudaStream_t stream) {
+    float* p = state;
+    int rc = stream_reset_rows(p, which, S, (size_t)7 * w.n_mels, stream);
+    if (rc) return rc;
+    p += (size_t)S * 7 * w.n_mels;
+    int new_rows = 1;
+    for (int i = 0; i < 4; ++i) {
+        const size_t per = (size_t)(kStreamHist[i] + new_rows) * (w.c0 >> i);
+        if ((rc = stream_reset_rows(p, which, S, per, stream))) return rc;
+        p += (size_t)S * per + 64;
+        new_rows *= w.rates[i];
+    }
+    return BVC_OK;
+}
+
+size_t vocoder_stream_workspace_floats(const VocoderWeights& w, int S) {
+    size_t n = (size_t)S * w.c0 + 256, x0 = 0;
+    int new_rows = 1;
+    for (int i = 0; i < 4; ++i) {
+        const int n_in = kStreamHist[i] + new_rows, C = w.c0 >> (i + 1);
+        const size_t n_out = (size_t)w.rates[i] * (n_in + 1);
+        n += 3 * ((size_t)S * n_out * C + 64);
+        x0 = std::max(x0, (size_t)S * n_out * C + (size_t)512 * C + 64);
+        new_rows *= w.rates[i];
+    }
+    return n + x0 + (size_t)S * 512 + 256;
+}
+
+// state: [mel ring S x 7 x X][ring 0][ring 1][ring 2][ring 3] (vocoder_stream_state_floats), zero = fresh streams.
+// mel_new [S, X]: the frame decoded in this hop; active [S] (nullable): streams that advance; wav_out [S, hop samples].
+int vocoder_stream_step(const VocoderWeights& w, Workspace& ws, float* state, const float* mel_new, int S,
+                        const unsigned char* active, float inv_scale_div, float* wav_out, int precision, cudaStream_t stream) {
+    if (w.n_stages != 4 || w.n_kernels != 3 || w.c0 != 128 || w.antialias[0] || w.antialias[1] || w.antialias[2] ||
+        w.antialias[3] || w.antialias_post) {
+        set_error("streaming vocoder: needs the shipped causal configuration without anti-aliased activations");
+        return BVC_ERR_INVALID;
+    }
+    if (precision < 1) { set_error("streaming vocoder: tensor-core mode only"); return BVC_ERR_INVALID; }
+    const int X = w.n_mels;
+    float* mel_ring = state;
+    float* ring[4];
+    int R[4], n_new[5];
+    {
+        float* p = state + (size_t)S * 7 * X;
+        n_new[0] = 1;
+        for (int i = 0; i < 4; ++i) {
+            R[i] = kStreamHist[i] + n_new[i];
+            ring[i] = p;
+            p += (size_t)S * R[i] * (w.c0 >> i) + 64;
+            n_new[i + 1] = n_new[i] * w.rates[i];
+        }
+    }
+    float* pre_new = ws.take((size_t)S * w.c0);
+    float* outs[4][3];
+    int n_out[4];
+    size_t x0n = 0;
+    for (int i = 0; i < 4; ++i) {
+        const int C = w.c0 >> (i + 1);
+        n_out[i] = w.rates[i] * (R[i] + 1);
+        for (int j = 0; j < 3; ++j) outs[i][j] = ws.take((size_t)S * n_out[i] * C);
+        x0n = std::max(x0n, (size_t)S * n_out[i] * C + (size_t)512 * C);
+    }
+    float* x0 = ws.take(x0n);
+    float* wav_v = ws.take((size_t)S * n_out[3]);
+    if (int rc = ws_check(ws, "vocoder_stream_step")) return rc;
+
+    auto push = [&](float* rg, int Rr, int C, const float* a, const float* b, const float* c, int parts, long long bstride, int row0,
+                    int nn) -> int {
+        ring_push_kernel<<<S, 256, (size_t)(Rr - nn) * C * sizeof(float), stream>>>(rg, Rr, C, a, b, c, parts, bstride, row0, nn, active);
+        BVC_CHECK_LAUNCH();
+        return BVC_OK;
+    };
+    // conv_pre (models.py:209-213): 7-tap causal conv = Linear over the 7 frames of the mel ring
+    int rc = push(mel_ring, 7, X, mel_new, mel_new, mel_new, 1, X, 0, 1);
+    if (rc) return rc;
+    {
+        LinearEpilogue ep;
+        ep.bias = w.b_pre;
+        ep.out = pre_new;
+        ep.ldo = w.c0;
+        if ((rc = linear_forward(mel_ring, 7 * X, S, w.pre, ep, precision, stream))) return rc;
+    }
+    if ((rc = push(ring[0], R[0], w.c0, pre_new, pre_new, pre_new, 1, w.c0, 0, 1))) return rc;
+    bool single_prev = true, post_done = false;
+    for (int i = 0; i < 4; ++i) {
+        const int C_in = w.c0 >> i, C = C_in / 2;
+        StageIn in;
+        in.n_parts = 1;
+        in.p[0] = in.p[1] = in.p[2] = ring[i];
+        in.bstride = (long long)R[i] * C_in;
+        in.n_in = R[i];
+        PostFuse pf;
+        pf.enable = true;
+        pf.inv_scale_div = inv_scale_div;
+        pf.wav = wav_v;
+        pf.length = n_out[3];
+        bool single = false;
+        if ((rc = run_plain_stage(w, i, in, n_out[i], x0, outs[i], S, precision, pf, &single, &post_done, stream))) return rc;
+        const int row0 = w.rates[i] * kStreamHist[i];          // first output row of the new hop
+        if (i < 3) {
+            if ((rc = push(ring[i + 1], R[i + 1], C, outs[i][0], outs[i][single ? 0 : 1], outs[i][single ? 0 : 2], single ? 1 : 3,
+                           (long long)n_out[i] * C, row0, n_new[i + 1])))
+                return rc;
+        }
+        single_prev = single;
+    }
+    (void)single_prev;
+    if (!post_done) { set_error("streaming vocoder: the fused tail did not run"); return BVC_ERR_STATE; }
+    stream_tail_kernel<<<S, 256, 0, stream>>>(wav_v, n_out[3], w.rates[3] * kStreamHist[3], n_new[4], active, wav_out);
+    BVC_CHECK_LAUNCH();
     return BVC_OK;
 }
 

@@ -199,6 +199,33 @@ int bvc_encode_host(bvc_handle* h, const float* x_host, int32_t B, int32_t L, fl
 int bvc_decode_host(bvc_handle* h, const float* codes_host, int32_t B, int32_t T, int32_t length,
                     float inv_scale_div, float* wav_host);
 
+/* ABI 3: streaming sessions (new; SURVEY.md 8f-1, BASELINE configs[4]).  n_streams independent streams advance hop by hop:
+ * one step = `hop` (256) new samples per stream = 11.61 ms of audio.  The reference has only the ingredients (h in / out at
+ * bvrnn.py:163,211; causal convolutions at third_party/BigVGAN/models.py:19-20,110,117; 768 samples of look-ahead in
+ * meldataset.py:76-80 = the 34.8 ms algorithmic latency of README.md:19).  The session owns the per-stream state:
+ * encoder: window FIFO (1024 samples), sample count, BVRNN state; decoder: BVRNN state, the vocoder's stage-input rings
+ * (15 k floats per stream).  Every step only enqueues work on `stream`.
+ *   active_dev / valid_dev  [n_streams] bytes or NULL (= all): streams that take part in this hop; idle streams keep their
+ *                           state untouched (ragged stream activity).
+ *   encode_step   x_new_dev [n_streams, hop] -> packed_out_dev [n_streams] wire words of the frame each stream completed in
+ *                 this hop, valid_out_dev [n_streams] = 1 where there is one (frame t needs 256 t + 768 samples: the first
+ *                 frame comes with the third hop and uses the reference's reflect padding of its own first samples;
+ *                 the right reflect padding of the offline call's last two frames is an end-of-utterance notion with no
+ *                 streaming counterpart: a stream simply ends).  bits_dev [n_streams] per-stream budgets or NULL -> scalar.
+ *   decode_step   packed_dev [n_streams] + valid_dev -> wav_out_dev [n_streams, hop] (zeros for idle streams).
+ *                 Edge policy: zero-state start -- the vocoder rings start at zero, so the first 27 frames of a stream
+ *                 (its 6 719-sample receptive field) differ from the offline decode, which zero-pads every convolution
+ *                 input at t < 0; from frame 27 on the samples are those of the offline bvc_decode_mel + bvc_vocode.
+ *   reset         zeroes the state of the streams marked in which_dev [n_streams] (NULL = all): a new stream starts. */
+typedef struct bvc_stream bvc_stream;
+int bvc_stream_create(bvc_handle* h, int32_t n_streams, bvc_stream** out);
+int bvc_stream_destroy(bvc_stream* st);
+int bvc_stream_reset(bvc_stream* st, const uint8_t* which_dev, void* stream);
+int bvc_stream_encode_step(bvc_stream* st, const float* x_new_dev, const uint8_t* active_dev, const float* bits_dev,
+                           float bits_scalar, float scale, uint64_t* packed_out_dev, uint8_t* valid_out_dev, void* stream);
+int bvc_stream_decode_step(bvc_stream* st, const uint64_t* packed_dev, const uint8_t* valid_dev, const float* bits_dev,
+                           float bits_scalar, float inv_scale_div, float* wav_out_dev, void* stream);
+
 /* Page-locked host memory for the host-buffer entry points above (cudaHostAlloc / cudaFreeHost).  Pinning a
  * 226 MB result buffer costs ~37 ms, so a binding should pool these blocks instead of allocating per call
  * (codec.py does: blocks return to its pool when the last tensor viewing them dies). */

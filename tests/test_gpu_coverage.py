@@ -343,3 +343,59 @@ def test_bitstream_wire_format(model_var, model_fix):
     s_fix = model_fix.encode_bitstream(x, 1000)
     assert model_fix.bitstream_header(s_fix[0])["n_bits"] == 64
     assert torch.equal(model_fix.decode_bitstream(s_fix, x.shape[1]), model_fix.decode(model_fix.encode(x, 1000), x.shape[1]))
+
+
+def test_stream_session_matches_offline(model_var):
+    """bvc_stream_*: hop-by-hop stateful encode / decode == the offline calls on interior frames, with the stated edge policy
+    (encoder: every frame whose window is complete, i.e. all but the offline call's last two right-reflected frames;
+    decoder: from frame 27 on -- zero-state start of the vocoder rings), ragged stream activity and per-stream reset."""
+    if model_var.precision == 0:
+        pytest.skip("the streaming session runs the tensor-core kernels only")
+    from bernoulli_var_speech_codec_b200.streaming import StreamSession
+    dev = model_var.device
+    S, N = 3, 70
+    x = _noise(S, 256 * N, 123).to(dev)
+    packed_off, bits = model_var.encode_packed(x, 3000)                     # T = N frames
+    sess = StreamSession(model_var, S, 3000)
+    words, valids, wavs = [], [], []
+    for k in range(N):
+        w, v = sess.encode_step(x[:, 256 * k:256 * (k + 1)])
+        words.append(w); valids.append(v)
+        wavs.append(sess.decode_step(w, v))
+    words, valids, wav = torch.stack(words, 1), torch.stack(valids, 1), torch.cat(wavs, 1)
+    assert bool((valids[:, :2] == 0).all()) and bool((valids[:, 2:] == 1).all())       # frame t arrives with hop t + 2
+    got = words[:, 2:]                                                                  # frames 0 .. N - 3
+    assert torch.equal(got, packed_off[:, :N - 2])
+    # decoder: offline decode of the same frames; the stream's hop k carries frame k - 2
+    T_s = N - 2
+    wav_off = model_var.decode_packed(packed_off[:, :T_s].contiguous(), bits, 256 * T_s)
+    wav_s = wav[:, 256 * 2:]
+    skip = 27 * 256
+    err = (wav_s[:, skip:] - wav_off[:, skip:]).abs().max().item()
+    assert err <= 1e-5, err
+    assert (wav_s[:, :skip] - wav_off[:, :skip]).abs().max().item() > 1e-4             # the stated start-up difference is real
+    assert bool((wav[:, :512] == 0).all())                                             # idle hops (no frame yet) give silence
+    # ragged activity: stream 1 pauses for 5 hops -> its output equals the dense run's, shifted; the others are unaffected
+    sess.reset()
+    wav2 = []
+    k_in = [0, 0, 0]
+    for step in range(N + 5):
+        active = torch.tensor([1, 0 if 20 <= step < 25 else 1, 1], dtype=torch.uint8)
+        xs = torch.stack([x[i, 256 * min(k_in[i], N - 1):256 * min(k_in[i], N - 1) + 256] for i in range(S)])
+        for i in range(S):
+            if active[i] and k_in[i] < N:
+                k_in[i] += 1
+            elif k_in[i] >= N:
+                active[i] = 0
+        w, v = sess.encode_step(xs, active=active)
+        wav2.append(sess.decode_step(w, v))
+    wav2 = torch.cat(wav2, 1)
+    assert torch.equal(wav2[0, :256 * N], wav[0]) and torch.equal(wav2[2, :256 * N], wav[2])
+    s1 = torch.cat([wav2[1, :256 * 20], wav2[1, 256 * 25:256 * (N + 5)]])
+    assert torch.equal(s1, wav[1])
+    assert bool((wav2[1, 256 * 20:256 * 25] == 0).all())
+    # reset of one stream: it starts over exactly like a fresh session, the others continue
+    sess.reset(torch.tensor([0, 1, 0], dtype=torch.uint8))
+    w, v = sess.encode_step(x[:, :256])
+    assert int(v[1]) == 0 and int(v[0]) == 1
+    sess.close()
