@@ -38,6 +38,17 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(out_path: str, extra_flags) -> str:
+    """A/B timing aid: the whole library rebuilt with extra nvcc flags (e.g. -DBVC_EPI_OLD) into out_path; load it with
+    BVC_LIBRARY=<out_path>."""
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-shared", "-o", out_path] + srcs + ["-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return out_path
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))

@@ -299,7 +299,11 @@ __device__ __forceinline__ float ex2_ftz(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#ifdef BVC_EPI_OLD
+__device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+#else
 __device__ __forceinline__ float elu_fast(float v) { return v > 0.f ? v : ex2_ftz(v * 1.4426950408889634f) - 1.f; }
+#endif
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 __device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 // tanh(v) = 1 - 2 / (1 + e^{2v}); saturates correctly: e^{2v} -> inf gives 1, -> 0 gives -1

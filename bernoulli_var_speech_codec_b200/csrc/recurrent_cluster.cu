@@ -64,6 +64,8 @@ struct Bars {
     uint64_t aFree;                // all MMAs of the job retired: activation buffer reusable
     uint64_t stgFull;              // the 3 peers' partials have landed in my staging buffer (expect_tx / st.async complete_tx)
     uint64_t stgEmpty;             // the 3 peers finished reading their staging buffer
+    uint64_t stgFullG[2];          // the same pair per epilogue group (multi-tile phases: the two 4-warp groups work on
+    uint64_t stgEmptyG[2];         // alternate tiles, each through its own half of the staging buffer)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -222,6 +224,14 @@ __device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sde
 
 // two fp32 values -> packed bf16 pairs (x = hi + lo), one packed conversion per part (cvt.rn.bf16x2.f32 d, hi_half, lo_half)
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+#ifdef BVC_EPI_OLD
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    return;
+#endif
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
     const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
@@ -568,6 +578,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
         mbar_init(&bars.aFree, 1);
         mbar_init(&bars.stgFull, 1);
         mbar_init(&bars.stgEmpty, 8 * (CLUSTER - 1));
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars.stgFullG[i], 1); mbar_init(&bars.stgEmptyG[i], 4 * (CLUSTER - 1)); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         if ((smem_u32(smem_dyn) & 1023u) != 0) atomicCAS(abort_flag, 0, 90);   // SWIZZLE_128B operands need 1 KiB alignment
         // this CTA's schedule
@@ -607,7 +618,12 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     tc_fence_after();
     const uint32_t tmem = ctl.tmem_slot;
     const bool bad_setup = *(volatile int*)abort_flag != 0;
+    // Register budget by role (the kernel is compiled for 384 threads x 168 registers): the warpgroup of the issue / copy /
+    // probe warps hands registers to the two epilogue warpgroups, whose tiles live in registers between tensor memory, the
+    // reduce-scatter and the fused epilogues.
 
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;\n");
     if (bad_setup) {
         // fall through to the common exit
     } else if (warp == 1) {
@@ -701,6 +717,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                 // of ALL its tiles with the A operand from tensor memory: shared memory then only serves the weights.  Same
                 // products in the same order, so the results are identical to the shared-memory form.
                 const bool use_ts = pl.n >= 2 && nck == 4 && !(dbg_flags & 1024);
+                long long tAcc = 0, tW = 0, tIss = 0, tPoll = 0;       // trace: clk spent per category in this phase
                 for (int j = 0; j < pl.n && !dead; ++j) {
                     const uint32_t e = ctl.ent[pl.e_off + j];
                     const int bn = ctl.ops[e >> 8].bn;
@@ -712,12 +729,14 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     if (stacked && (accIt & 1)) ++accIt;
                     const int slot = accIt % ACC_SLOTS;
                     accIt += stacked ? 2 : 1;
+                    long long tq = clock64();
                     for (int q = 0; q < (stacked ? 2 : 1) && !dead; ++q) {
                         const uint32_t bit = 1u << (slot + q);
                         if ((accUsed & bit) && !mbar_wait<false>(&bars.accEmpty[slot + q], (accPar >> (slot + q)) & 1u, abort_flag, 21)) dead = true;
                         if (accUsed & bit) accPar ^= bit;
                         accUsed |= bit;
                     }
+                    tAcc += clock64() - tq;
                     if (dead) break;
                     tc_fence_after();
                     const uint32_t idesc = make_idesc(TILE_M, bn), idesc2 = make_idesc(TILE_M, 2 * bn);
@@ -725,9 +744,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     // The tensor pipe runs dry whenever this warp is not issuing (an MMA issues in ~55 clk and executes in ~72), so
                     // the chunks that have already landed are found with one batch of polls instead of one blocking wait each.
                     uint32_t okW = 0, okA = j == 0 ? 0u : 0xFu;
+                    tq = clock64();
 #pragma unroll
                     for (int i = 0; i < A_SLOTS; ++i)
                         if (i < nck) okW |= mbar_test(&bars.fullW[(wIt + i) % W_SLOTS], ((wIt + i) / W_SLOTS) & 1u) << i;
+                    tPoll += clock64() - tq;
                     for (int c = 0; c < nck; ++c) {
                         if (j == 0) {
                             if (!((okA >> c) & 1u) && !mbar_wait<false>(&bars.fullA[c], (aPar >> c) & 1u, abort_flag, 22)) { dead = true; break; }
@@ -741,9 +762,12 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             if (lane == 0 && c == nck - 1) BVC_TRACE(6);
                         }
                         const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
+                        tq = clock64();
                         if (!((okW >> c) & 1u) && !mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
+                        tW += clock64() - tq;
                         ++wIt;
                         tc_fence_after();
+                        tq = clock64();
                         if (use_ts) {
                             if (elect_one()) {
                                 const uint64_t dah = descA + (uint64_t)((c * ACT_CHUNK_BYTES) >> 4);
@@ -798,6 +822,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             if (c == nck - 1) umma_commit(&bars.accFull[slot]);
                         }
                         __syncwarp();
+                        tIss += clock64() - tq;
                     }
                     if (dead) break;
                 }
@@ -805,6 +830,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     if (elect_one()) umma_commit(&bars.aFree);
                     __syncwarp();
                     if (lane == 0) BVC_TRACE(7);
+                    if (lane == 0 && trace && t < trace_frames) {
+                        unsigned long long* tr = trace + (((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS;
+                        tr[24] = (unsigned long long)tAcc; tr[25] = (unsigned long long)tW; tr[26] = (unsigned long long)tIss;
+                        tr[27] = (unsigned long long)tPoll;
+                    }
                 }
             }
         }
@@ -828,7 +858,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     }
                 }
         }
-    } else if (warp >= 4) {
+    }
+    } else if (bad_setup) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;\n");
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;\n");
         // =========================== epilogue warps ===========================
         // 8 warps: warp % 4 = TMEM lane quadrant (rows 32 q .. 32 q + 31), hf = (warp - 4) / 4 = column half.  A 64-wide
         // tile is finished by two threads per row (8 of the 16 columns this CTA owns after the reduce-scatter each); the
@@ -840,11 +874,17 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
         const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
         const uint32_t stg_send = smem_base + SMEM_STG;
         const unsigned char* stg_recv = smem_gen + SMEM_STG;
-        uint32_t accIt = 0, sIt = 0, fullPar = 0;      // fullPar: per slot, parity of the next accFull completion
+        uint32_t accIt = 0, sIt = 0, sItG = 0, fullPar = 0;      // fullPar: per slot, parity of the next accFull completion
         bool dead = false;
         for (int t = 0; t < T && !dead; ++t) {
             for (int ph = 0; ph < n_phases && !dead; ++ph) {
                 const PhaseLocal& pl = ctl.ph[ph];
+                // A CTA with several 64-wide tiles in the phase is bound by this epilogue (tensor-memory read, reduce-scatter
+                // round trip, finalisation: ~4 400 clk per tile against ~2 400 clk of MMAs, profiles/r02_recurrent_trace_clk_*).
+                // There the two 4-warp groups take ALTERNATE tiles (group = tile parity) instead of halving one tile: each
+                // group runs the two 8-column halves of its tile one after the other through its own half of the staging
+                // buffer and its own pair of barriers, so two tiles are in the epilogue at any time.
+                const bool gmode = pl.n >= 2 && pl.split && !(dbg_flags & 16384);
                 for (int j = 0; j < pl.n && !dead; ++j) {
                     const uint32_t e = ctl.ent[pl.e_off + j];
                     const Op& op = ctl.ops[e >> 8];
@@ -895,6 +935,57 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                                 if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)p));
                         }
                         if (hf == 0) finalize_gru(fr, t, m, row, m_tile, u0, v, pf);
+                        continue;
+                    }
+                    if (gmode) {
+                        // ---- 64-wide split tile in a multi-tile phase: this group's tile, thread = row, 2 x 8 columns ----
+                        const int g = hf;
+                        if ((j & 1) != g) continue;      // the other group's tile (slot and parity bookkeeping is done above)
+                        Prefetch8 pf;
+                        prefetch8(op, fr, t, m, nt * 64 + 16 * rank, pf);
+                        if (!mbar_wait<false>(&bars.accFull[slot], full_parity, abort_flag, 31)) { dead = true; break; }
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int hh = 0; hh < 2 && !dead; ++hh) {
+                            float acc[32], own[8], v[8];
+#pragma unroll
+                            for (int p = 0; p < CLUSTER; ++p) tmem_ld8(taddr + 16 * p + 8 * hh, acc + 8 * p);
+                            tmem_ld_wait();
+                            if (stacked) {
+#pragma unroll
+                                for (int p = 0; p < CLUSTER; p += 2) {
+                                    float aux[16];
+                                    tmem_ld8(taddr + 64 + 16 * p + 8 * hh, aux);
+                                    tmem_ld8(taddr + 64 + 16 * (p + 1) + 8 * hh, aux + 8);
+                                    tmem_ld_wait();
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) acc[8 * p + i] += aux[i];
+                                }
+                            }
+                            if (hh == 1) {           // the accumulator is drained: 4 warps stand in for the barrier's 8 arrivals
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    mbar_arrive(&bars.accEmpty[slot]); mbar_arrive(&bars.accEmpty[slot]);
+                                    if (stacked) { mbar_arrive(&bars.accEmpty[slot + 1]); mbar_arrive(&bars.accEmpty[slot + 1]); }
+                                }
+                            }
+                            const int sr = sItG;
+                            ++sItG;
+                            if (sr >= 1 && !mbar_wait<false>(&bars.stgEmptyG[g], (sr - 1) & 1, abort_flag, 34)) { dead = true; break; }
+                            if (quad == 0 && lane == 0) mbar_expect_tx(&bars.stgFullG[g], (uint32_t)((CLUSTER - 1) * TILE_M * 8 * 4));
+                            exchange8(acc, rank, g, row, stg_send, smem_u32(&bars.stgFullG[g]), own);
+                            if (!mbar_wait<false>(&bars.stgFullG[g], sr & 1, abort_flag, 35)) { dead = true; break; }
+                            reduce_parts8(own, rank, g, row, stg_recv, v);
+                            __syncwarp();
+                            if (lane == 0) {
+#pragma unroll
+                                for (int p = 0; p < CLUSTER; ++p)
+                                    if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmptyG[g]), (uint32_t)p));
+                            }
+                            finalize8(op, fr, t, m, row, m_tile, nt * 64 + 16 * rank + 8 * hh, v, pf);
+                            if (hh == 0) prefetch8(op, fr, t, m, nt * 64 + 16 * rank + 8, pf);    // lands under the second half's exchange
+                        }
                         continue;
                     }
                     // ---- 64-wide split tile (or 16-wide full-K tile): two threads per row, 8 columns each ----

@@ -27,13 +27,16 @@ if CLK:
     for ph in range(n_ph):
         if np.all(np.isnan(fr[:, ph, 13])):
             continue
-        busy = ~np.isnan(fr[:, ph, 8]) & ~np.isnan(fr[:, ph, 2])
+        busy = ~np.isnan(fr[:, ph, 7]) & ~np.isnan(fr[:, ph, 2])
         if not busy.any():
             continue
         ref = fr[busy, ph, 2]
         med = [np.nanmedian(fr[busy, ph, e] - ref) if e < n_ev else np.nan for _, e in ev]
         mx = [np.nanmax(fr[busy, ph, e] - ref) if e < n_ev else np.nan for _, e in ev]
         print("%3d  %4d  | " % (ph, int(busy.sum())) + " ".join("%6.0f" % v for v in med))
+        if n_ev > 27:
+            print("       MMA warp clk in: accEmpty waits %.0f, weight waits %.0f, issue regions %.0f, weight polls %.0f (median)" % tuple(
+                np.nanmedian(fr[busy, ph, e]) for e in (24, 25, 26, 27)))
         print("       max | " + " ".join("%6.0f" % v for v in mx))
     sys.exit(0)
 prev_done = np.nanmax(d[:, frame - 1, :, 13]) if frame > 0 else np.nanmin(fr[:, 0, 0])
