@@ -41,12 +41,9 @@ constexpr int kThreads = 384;                                // MMA warp, copy w
 constexpr int A_SLOTS = 4;                                   // chunks of the resident activation quarter
 constexpr int W_SLOTS = 4;
 constexpr int W_SLOT_BYTES = 2 * 64 * 128;                   // bn <= 64
-constexpr int ACC_SLOTS = 4;
+constexpr int ACC_SLOTS = 8;
 constexpr int ACC_COLS = 64;
-constexpr int TMEM_COLS = 512;                               // the whole tensor memory of the SM:
-constexpr int TMEM_A_HI = ACC_SLOTS * ACC_COLS;              //   columns 0 .. 255 accumulator slots, 256 .. 383 the hi part and
-constexpr int TMEM_A_LO = TMEM_A_HI + 128;                   //   384 .. 511 the lo part of the resident activation quarter
-                                                             //   (128 rows x 256 K as bf16 pairs: 8 columns per k16 step)
+constexpr int TMEM_COLS = ACC_SLOTS * ACC_COLS;              // 512: the whole tensor memory of the SM
 constexpr int STG_SENDER_BYTES = 4 * TILE_M * 16;            // [4 column quads][128 rows][16 bytes]
 constexpr int STG_BUF_BYTES = (CLUSTER - 1) * STG_SENDER_BYTES;
 constexpr int SMEM_A = 0;
@@ -64,8 +61,6 @@ struct Bars {
     uint64_t aFree;                // all MMAs of the job retired: activation buffer reusable
     uint64_t stgFull;              // the 3 peers' partials have landed in my staging buffer (expect_tx / st.async complete_tx)
     uint64_t stgEmpty;             // the 3 peers finished reading their staging buffer
-    uint64_t stgFullG[2];          // the same pair per epilogue group (multi-tile phases: the two 4-warp groups work on
-    uint64_t stgEmptyG[2];         // alternate tiles, each through its own half of the staging buffer)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -207,21 +202,6 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
         : "memory");
 }
 
-// A operand from tensor memory (lane = row, 8 columns per k16 step), B from shared memory
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// shared -> tensor memory: 128 rows x 32 bytes (one k16 step of a K-major SWIZZLE_128B operand, addressed by the MMA's own
-// descriptor) into 8 columns; runs in the tensor pipe, in issue order with the MMAs of the same thread
-__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;\n" ::"r"(tmem_dst), "l"(sdesc) : "memory");
-}
-
 // two fp32 values -> packed bf16 pairs (x = hi + lo), one packed conversion per part (cvt.rn.bf16x2.f32 d, hi_half, lo_half)
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
 #ifdef BVC_EPI_OLD
@@ -248,14 +228,22 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(v));
     return v;
 }
+// Phase trace (bring-up): compiled in only with -DBVC_REC_TRACING (tools/build_kernel_variant.sh / build.build_variant), because
+// even the disabled checks cost ~4 % per frame in the latency-critical issue warp (measured A/B on one B200).
 // debug flag 64: stamps are the SM's clock64 (exact intervals inside one CTA) instead of %globaltimer (comparable across CTAs,
 // but it ticks in steps of ~0.26 us on this part)
+#ifdef BVC_REC_TRACING
 #define BVC_TRACE(ev)                                                                                             \
     do {                                                                                                          \
         if (trace && t < trace_frames)                                                                            \
             trace[(((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS + (ev)] =            \
                 (dbg_flags & 64) ? (unsigned long long)clock64() : global_ns();                                   \
     } while (0)
+#define BVC_TRACING(x) x
+#else
+#define BVC_TRACE(ev) do { } while (0)
+#define BVC_TRACING(x)
+#endif
 
 // loads that may have been written by another CTA in an earlier phase go through L2 (ld.cg)
 __device__ __forceinline__ void load16_cg(const float* p, float* v) {
@@ -444,7 +432,7 @@ __device__ __forceinline__ void finalize8(const Op& op, const Frame& fr, int t, 
     if (m >= fr.M) return;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += pf.a[i];
-    if (tr) tr[20] = (unsigned long long)clock64();
+    BVC_TRACING(if (tr) tr[20] = (unsigned long long)clock64();)
     if (op.kind == KIND_BOTTLENECK) {
         // z = round(sigmoid(logit)), masked to 0.5 beyond the frame's bit budget (bvrnn.py:191-196)
         float code[8];
@@ -459,8 +447,11 @@ __device__ __forceinline__ void finalize8(const Op& op, const Frame& fr, int t, 
         for (int i = 0; i < 8; ++i) {
             const bool active = !fr.var_bit || (pf.budget > (float)(col0 + i));
             // greedy: round(p) (half to even: p == 0.5 -> 0);  sampled: round((u - 0.5) + p) in the reference's fp32 order
-            const float p = sigmoidf_(v[i]);
-            const bool bit = active && (fr.uniforms ? (rintf((u[i] - 0.5f) + p) == 1.f) : (p > 0.5f));
+            bool bit = false;
+            if (active) {
+                const float p = sigmoidf_(v[i]);
+                bit = fr.uniforms ? (rintf((u[i] - 0.5f) + p) == 1.f) : (p > 0.5f);
+            }
             code[i] = active ? (bit ? 1.f : 0.f) : 0.5f;
             if (bit) word |= 1u << i;
         }
@@ -475,7 +466,7 @@ __device__ __forceinline__ void finalize8(const Op& op, const Frame& fr, int t, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = elu_fast(v[i]);
     }
-    if (tr) tr[21] = (unsigned long long)clock64();
+    BVC_TRACING(if (tr) tr[21] = (unsigned long long)clock64();)
     if (op.kind == KIND_MEL) {
         if (fr.mel_out) {
             float* mo = fr.mel_out + ((size_t)m * fr.T + t) * fr.X;
@@ -487,9 +478,9 @@ __device__ __forceinline__ void finalize8(const Op& op, const Frame& fr, int t, 
         return;
     }
     if (op.out_img && col0 < op.N) store_img8(op.out_img, m_tile, op.out_kchunks, row, col0, v, false);
-    if (tr) tr[22] = (unsigned long long)clock64();
+    BVC_TRACING(if (tr) tr[22] = (unsigned long long)clock64();)
     if (op.out_f && col0 < op.N) store8(op.out_f + (size_t)m * op.ldo + col0, v);
-    if (tr) tr[23] = (unsigned long long)clock64();
+    BVC_TRACING(if (tr) tr[23] = (unsigned long long)clock64();)
 }
 // Reduce-scatter of a 128 x 64 partial tile with two threads per row: acc = this thread's 8 columns of each of the four
 // quarters (quarter p at acc[8 p]); staging quads 2 hf, 2 hf + 1 of every sender belong to column half hf.
@@ -578,7 +569,6 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
         mbar_init(&bars.aFree, 1);
         mbar_init(&bars.stgFull, 1);
         mbar_init(&bars.stgEmpty, 8 * (CLUSTER - 1));
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars.stgFullG[i], 1); mbar_init(&bars.stgEmptyG[i], 4 * (CLUSTER - 1)); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         if ((smem_u32(smem_dyn) & 1023u) != 0) atomicCAS(abort_flag, 0, 90);   // SWIZZLE_128B operands need 1 KiB alignment
         // this CTA's schedule
@@ -618,12 +608,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     tc_fence_after();
     const uint32_t tmem = ctl.tmem_slot;
     const bool bad_setup = *(volatile int*)abort_flag != 0;
-    // Register budget by role (the kernel is compiled for 384 threads x 168 registers): the warpgroup of the issue / copy /
-    // probe warps hands registers to the two epilogue warpgroups, whose tiles live in registers between tensor memory, the
-    // reduce-scatter and the fused epilogues.
-
     if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 136;\n");
     if (bad_setup) {
         // fall through to the common exit
     } else if (warp == 1) {
@@ -710,14 +695,6 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
             for (int ph = 0; ph < n_phases && !dead; ++ph) {
                 const PhaseLocal& pl = ctl.ph[ph];
                 const int nck = pl.nck;
-                // A CTA with several tiles in the phase reads its activation quarter once per tile.  The MMA stage is bound by
-                // shared-memory bandwidth (operand fetch of the MMAs + the bulk copies landing: measured in place at twice the
-                // isolated MMA time, tools/umma_bench.cu), and the 128 x 16 activation operand is the larger part of every fetch.
-                // Such a phase copies each activation chunk to tensor memory once (tcgen05.cp, 8 per chunk) and issues the MMAs
-                // of ALL its tiles with the A operand from tensor memory: shared memory then only serves the weights.  Same
-                // products in the same order, so the results are identical to the shared-memory form.
-                const bool use_ts = pl.n >= 2 && nck == 4 && !(dbg_flags & 1024);
-                long long tAcc = 0, tW = 0, tIss = 0, tPoll = 0;       // trace: clk spent per category in this phase
                 for (int j = 0; j < pl.n && !dead; ++j) {
                     const uint32_t e = ctl.ent[pl.e_off + j];
                     const int bn = ctl.ops[e >> 8].bn;
@@ -729,77 +706,32 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     if (stacked && (accIt & 1)) ++accIt;
                     const int slot = accIt % ACC_SLOTS;
                     accIt += stacked ? 2 : 1;
-                    long long tq = clock64();
                     for (int q = 0; q < (stacked ? 2 : 1) && !dead; ++q) {
                         const uint32_t bit = 1u << (slot + q);
                         if ((accUsed & bit) && !mbar_wait<false>(&bars.accEmpty[slot + q], (accPar >> (slot + q)) & 1u, abort_flag, 21)) dead = true;
                         if (accUsed & bit) accPar ^= bit;
                         accUsed |= bit;
                     }
-                    tAcc += clock64() - tq;
                     if (dead) break;
                     tc_fence_after();
                     const uint32_t idesc = make_idesc(TILE_M, bn), idesc2 = make_idesc(TILE_M, 2 * bn);
                     const uint32_t d_tmem = tmem + slot * ACC_COLS;
                     // The tensor pipe runs dry whenever this warp is not issuing (an MMA issues in ~55 clk and executes in ~72), so
                     // the chunks that have already landed are found with one batch of polls instead of one blocking wait each.
-                    uint32_t okW = 0, okA = j == 0 ? 0u : 0xFu;
-                    tq = clock64();
-#pragma unroll
-                    for (int i = 0; i < A_SLOTS; ++i)
-                        if (i < nck) okW |= mbar_test(&bars.fullW[(wIt + i) % W_SLOTS], ((wIt + i) / W_SLOTS) & 1u) << i;
-                    tPoll += clock64() - tq;
+                    // (no batched polls of the chunk barriers here: a poll of a completed barrier costs ~130 clk on this warp's
+                    //  critical path, a blocking wait on one ~100; measured 1 % per frame)
                     for (int c = 0; c < nck; ++c) {
                         if (j == 0) {
-                            if (!((okA >> c) & 1u) && !mbar_wait<false>(&bars.fullA[c], (aPar >> c) & 1u, abort_flag, 22)) { dead = true; break; }
-                            if (c == 0) {
-#pragma unroll
-                                for (int i = 1; i < A_SLOTS; ++i)
-                                    if (i < nck) okA |= mbar_test(&bars.fullA[i], (aPar >> i) & 1u) << i;
-                            }
+                            if (!mbar_wait<false>(&bars.fullA[c], (aPar >> c) & 1u, abort_flag, 22)) { dead = true; break; }
                             aPar ^= 1u << c;
                             if (lane == 0 && c == 0) BVC_TRACE(5);
                             if (lane == 0 && c == nck - 1) BVC_TRACE(6);
                         }
                         const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
-                        tq = clock64();
-                        if (!((okW >> c) & 1u) && !mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
-                        tW += clock64() - tq;
+                        if (!mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
                         ++wIt;
                         tc_fence_after();
-                        tq = clock64();
-                        if (use_ts) {
-                            if (elect_one()) {
-                                const uint64_t dah = descA + (uint64_t)((c * ACT_CHUNK_BYTES) >> 4);
-                                const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
-                                const uint64_t dwh = descW + (uint64_t)((ws * W_SLOT_BYTES) >> 4);
-                                const uint64_t dwl = dwh + (uint64_t)((bn * 128) >> 4);
-                                const uint32_t th = tmem + TMEM_A_HI + c * 32, tl = tmem + TMEM_A_LO + c * 32;
-                                if (j == 0) {
-#pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) {
-                                        tmem_cp_128x256b(th + 8 * ks, dah + 2 * ks);
-                                        tmem_cp_128x256b(tl + 8 * ks, dal + 2 * ks);
-                                    }
-                                }
-                                if (stacked) {
-#pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) {
-                                        umma_ts(d_tmem, th + 8 * ks, dwh + 2 * ks, idesc2, (c | ks) != 0 ? 1u : 0u);
-                                        umma_ts(d_tmem, tl + 8 * ks, dwh + 2 * ks, idesc, 1u);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) {   // small terms first
-                                        umma_ts(d_tmem, tl + 8 * ks, dwh + 2 * ks, idesc, (c | ks) != 0 ? 1u : 0u);
-                                        umma_ts(d_tmem, th + 8 * ks, dwl + 2 * ks, idesc, 1u);
-                                        umma_ts(d_tmem, th + 8 * ks, dwh + 2 * ks, idesc, 1u);
-                                    }
-                                }
-                                umma_commit(&bars.emptyW[ws]);
-                                if (c == nck - 1) umma_commit(&bars.accFull[slot]);
-                            }
-                        } else if (elect_one()) {
+                        if (elect_one()) {
                             const uint64_t dah = descA + (uint64_t)((c * ACT_CHUNK_BYTES) >> 4);
                             const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
                             const uint64_t dwh = descW + (uint64_t)((ws * W_SLOT_BYTES) >> 4);
@@ -822,7 +754,6 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             if (c == nck - 1) umma_commit(&bars.accFull[slot]);
                         }
                         __syncwarp();
-                        tIss += clock64() - tq;
                     }
                     if (dead) break;
                 }
@@ -830,11 +761,6 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     if (elect_one()) umma_commit(&bars.aFree);
                     __syncwarp();
                     if (lane == 0) BVC_TRACE(7);
-                    if (lane == 0 && trace && t < trace_frames) {
-                        unsigned long long* tr = trace + (((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS;
-                        tr[24] = (unsigned long long)tAcc; tr[25] = (unsigned long long)tW; tr[26] = (unsigned long long)tIss;
-                        tr[27] = (unsigned long long)tPoll;
-                    }
                 }
             }
         }
@@ -842,6 +768,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
         // =========================== trace probe (bring-up only) ===========================
         // An otherwise idle warp watches the activation-chunk barriers and stamps when each chunk has landed, independent
         // of the MMA warp's own progress (events 16 + c).
+#ifdef BVC_REC_TRACING
         if (trace && lane == 0) {
             uint32_t aPar = 0;
             for (int t = 0; t < T && t < trace_frames; ++t)
@@ -858,11 +785,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     }
                 }
         }
+#endif
     }
     } else if (bad_setup) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;\n");
+        // fall through to the common exit
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;\n");
         // =========================== epilogue warps ===========================
         // 8 warps: warp % 4 = TMEM lane quadrant (rows 32 q .. 32 q + 31), hf = (warp - 4) / 4 = column half.  A 64-wide
         // tile is finished by two threads per row (8 of the 16 columns this CTA owns after the reduce-scatter each); the
@@ -874,17 +801,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
         const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
         const uint32_t stg_send = smem_base + SMEM_STG;
         const unsigned char* stg_recv = smem_gen + SMEM_STG;
-        uint32_t accIt = 0, sIt = 0, sItG = 0, fullPar = 0;      // fullPar: per slot, parity of the next accFull completion
+        uint32_t accIt = 0, sIt = 0, fullPar = 0;      // fullPar: per slot, parity of the next accFull completion
         bool dead = false;
         for (int t = 0; t < T && !dead; ++t) {
             for (int ph = 0; ph < n_phases && !dead; ++ph) {
                 const PhaseLocal& pl = ctl.ph[ph];
-                // A CTA with several 64-wide tiles in the phase is bound by this epilogue (tensor-memory read, reduce-scatter
-                // round trip, finalisation: ~4 400 clk per tile against ~2 400 clk of MMAs, profiles/r02_recurrent_trace_clk_*).
-                // There the two 4-warp groups take ALTERNATE tiles (group = tile parity) instead of halving one tile: each
-                // group runs the two 8-column halves of its tile one after the other through its own half of the staging
-                // buffer and its own pair of barriers, so two tiles are in the epilogue at any time.
-                const bool gmode = pl.n >= 2 && pl.split && !(dbg_flags & 16384);
                 for (int j = 0; j < pl.n && !dead; ++j) {
                     const uint32_t e = ctl.ent[pl.e_off + j];
                     const Op& op = ctl.ops[e >> 8];
@@ -935,57 +856,6 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                                 if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)p));
                         }
                         if (hf == 0) finalize_gru(fr, t, m, row, m_tile, u0, v, pf);
-                        continue;
-                    }
-                    if (gmode) {
-                        // ---- 64-wide split tile in a multi-tile phase: this group's tile, thread = row, 2 x 8 columns ----
-                        const int g = hf;
-                        if ((j & 1) != g) continue;      // the other group's tile (slot and parity bookkeeping is done above)
-                        Prefetch8 pf;
-                        prefetch8(op, fr, t, m, nt * 64 + 16 * rank, pf);
-                        if (!mbar_wait<false>(&bars.accFull[slot], full_parity, abort_flag, 31)) { dead = true; break; }
-                        tc_fence_after();
-#pragma unroll 1
-                        for (int hh = 0; hh < 2 && !dead; ++hh) {
-                            float acc[32], own[8], v[8];
-#pragma unroll
-                            for (int p = 0; p < CLUSTER; ++p) tmem_ld8(taddr + 16 * p + 8 * hh, acc + 8 * p);
-                            tmem_ld_wait();
-                            if (stacked) {
-#pragma unroll
-                                for (int p = 0; p < CLUSTER; p += 2) {
-                                    float aux[16];
-                                    tmem_ld8(taddr + 64 + 16 * p + 8 * hh, aux);
-                                    tmem_ld8(taddr + 64 + 16 * (p + 1) + 8 * hh, aux + 8);
-                                    tmem_ld_wait();
-#pragma unroll
-                                    for (int i = 0; i < 16; ++i) acc[8 * p + i] += aux[i];
-                                }
-                            }
-                            if (hh == 1) {           // the accumulator is drained: 4 warps stand in for the barrier's 8 arrivals
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) {
-                                    mbar_arrive(&bars.accEmpty[slot]); mbar_arrive(&bars.accEmpty[slot]);
-                                    if (stacked) { mbar_arrive(&bars.accEmpty[slot + 1]); mbar_arrive(&bars.accEmpty[slot + 1]); }
-                                }
-                            }
-                            const int sr = sItG;
-                            ++sItG;
-                            if (sr >= 1 && !mbar_wait<false>(&bars.stgEmptyG[g], (sr - 1) & 1, abort_flag, 34)) { dead = true; break; }
-                            if (quad == 0 && lane == 0) mbar_expect_tx(&bars.stgFullG[g], (uint32_t)((CLUSTER - 1) * TILE_M * 8 * 4));
-                            exchange8(acc, rank, g, row, stg_send, smem_u32(&bars.stgFullG[g]), own);
-                            if (!mbar_wait<false>(&bars.stgFullG[g], sr & 1, abort_flag, 35)) { dead = true; break; }
-                            reduce_parts8(own, rank, g, row, stg_recv, v);
-                            __syncwarp();
-                            if (lane == 0) {
-#pragma unroll
-                                for (int p = 0; p < CLUSTER; ++p)
-                                    if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmptyG[g]), (uint32_t)p));
-                            }
-                            finalize8(op, fr, t, m, row, m_tile, nt * 64 + 16 * rank + 8 * hh, v, pf);
-                            if (hh == 0) prefetch8(op, fr, t, m, nt * 64 + 16 * rank + 8, pf);    // lands under the second half's exchange
-                        }
                         continue;
                     }
                     // ---- 64-wide split tile (or 16-wide full-K tile): two threads per row, 8 columns each ----
@@ -1058,9 +928,13 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         __syncwarp();
                         release_acc();
                     }
+#ifdef BVC_REC_TRACING
                     finalize8(op, fr, t, m, row, m_tile, col0, v, pf,
                               (trace && t < trace_frames && tid == 128 && j == pl.n - 1 && (dbg_flags & 64))
                                   ? trace + (((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS : nullptr);
+#else
+                    finalize8(op, fr, t, m, row, m_tile, col0, v, pf);
+#endif
                 }
                 // ---- end of phase: publish this CTA's outputs to the m-tile's barrier domain ----
                 if (tid == 128) BVC_TRACE(12);
