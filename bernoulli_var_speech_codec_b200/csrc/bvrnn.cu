@@ -322,6 +322,11 @@ struct ProgramBuilder {
     // Clusters are dealt to m-tiles in contiguous, equal blocks (an m-tile is a barrier domain); the n-tiles
     // of a phase's ops are dealt round-robin to the clusters of each m-tile.
     bool finish() {
+        if (const char* e = getenv("BVC_REC_STACK_ALL")) {       // experiment: every non-GRU layer as [main | aux]
+            if (atoi(e))
+                for (int i = 0; i < p->n_ops; ++i)
+                    if (p->ops[i].kind != rec::KIND_GRU && p->ops[i].bn == 64) p->ops[i].stack = 1;
+        }
         const int n_mt = (M + rec::TILE_M - 1) / rec::TILE_M;
         if (n_mt > n_clusters || n_mt > rec::MAX_MTILES || (int)phases.size() > rec::MAX_PHASES) return false;
         p->n_clusters = n_clusters;

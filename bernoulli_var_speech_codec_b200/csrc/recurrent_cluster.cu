@@ -560,7 +560,9 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     unsigned* counter = sync_words + 32 * (1 + m_tile);
     unsigned long long* trace = prog->trace;
     const int trace_frames = prog->trace_frames;
-    const int dbg_flags = prog->debug_flags;
+    const int dbg_flags = prog->debug_flags;   // BVC_REC_DEBUG: timing probes 2048 no exchange, 4096 no weight copies, 8192 no MMAs, 16384 no
+                                               // epilogue maths, 32768 no activation copies, 131072 no GRU operand loads (all give wrong
+                                               // results; profiles/r02_recurrent_probes.txt), 64 clock64 trace stamps
 
     if (tid == 0) {
         for (int i = 0; i < A_SLOTS; ++i) mbar_init(&bars.fullA[i], 1);
@@ -669,6 +671,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             asm volatile("fence.proxy.async.global;\n" ::: "memory");
                             for (int c = 0; c < nck; ++c) {
                                 const int cs = nck == 4 ? ((c + rot) & 3) : c;
+                                if (dbg_flags & 32768) { mbar_arrive(&bars.fullA[c]); continue; }   // timing probe (wrong results): no activation copy
                                 mbar_expect_tx(&bars.fullA[c], ACT_CHUNK_BYTES);
                                 bulk_g2s(smem_base + SMEM_A + c * ACT_CHUNK_BYTES, src + (size_t)cs * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES,
                                          &bars.fullA[c]);
@@ -736,7 +739,9 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
                             const uint64_t dwh = descW + (uint64_t)((ws * W_SLOT_BYTES) >> 4);
                             const uint64_t dwl = dwh + (uint64_t)((bn * 128) >> 4);
-                            if (stacked) {
+                            if (dbg_flags & 8192) {
+                                // timing probe (wrong results): no MMAs, only the commits
+                            } else if (stacked) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
                                     umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc2, (c | ks) != 0 ? 1u : 0u);
@@ -827,7 +832,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         // ---- 48-wide tile: thread = row, 12 columns = r, z, n of 4 hidden units ----
                         const int col0 = nt * 48 + 12 * rank, u0 = nt * 16 + 4 * rank;
                         Prefetch pf;
-                        if (hf == 0) prefetch_epilogue(op, fr, t, m, col0, u0, pf);
+                        if (hf == 0 && !(dbg_flags & 131072)) prefetch_epilogue(op, fr, t, m, col0, u0, pf);   // probe 131072 (wrong results): no GRU operand loads
                         if (!mbar_wait<false>(&bars.accFull[slot], full_parity, abort_flag, 31)) { dead = true; break; }
                         tc_fence_after();
                         const int sr = sIt;
@@ -850,11 +855,8 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             if (!mbar_wait<false>(&bars.stgFull, sr & 1, abort_flag, 33)) { dead = true; break; }
                         }
                         __syncwarp();
-                        if (lane == 0) {
-#pragma unroll
-                            for (int p = 0; p < CLUSTER; ++p)
-                                if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)p));
-                        }
+                        // one lane per peer: the three remote arrivals leave together instead of one after the other
+                        if (lane < CLUSTER && lane != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)lane));
                         if (hf == 0) finalize_gru(fr, t, m, row, m_tile, u0, v, pf);
                         continue;
                     }
@@ -908,11 +910,8 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         reduce_parts8(own, rank, hf, row, stg_recv, v);
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(15);
                         __syncwarp();
-                        if (lane == 0) {
-#pragma unroll
-                            for (int p = 0; p < CLUSTER; ++p)
-                                if (p != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)p));
-                        }
+                        // one lane per peer: the three remote arrivals leave together instead of one after the other
+                        if (lane < CLUSTER && lane != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)lane));
                         if (tid == 128 && j == pl.n - 1) BVC_TRACE(1);
                     } else {
                         tmem_ld8(taddr + 8 * hf, v);
@@ -933,7 +932,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                               (trace && t < trace_frames && tid == 128 && j == pl.n - 1 && (dbg_flags & 64))
                                   ? trace + (((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS : nullptr);
 #else
-                    finalize8(op, fr, t, m, row, m_tile, col0, v, pf);
+                    if (!(dbg_flags & 16384)) finalize8(op, fr, t, m, row, m_tile, col0, v, pf);   // probe 16384: no epilogue math / stores
 #endif
                 }
                 // ---- end of phase: publish this CTA's outputs to the m-tile's barrier domain ----
