@@ -49,8 +49,10 @@ constexpr int STG_BUF_BYTES = (CLUSTER - 1) * STG_SENDER_BYTES;
 constexpr int SMEM_A = 0;
 constexpr int SMEM_W = SMEM_A + A_SLOTS * ACT_CHUNK_BYTES;
 constexpr int SMEM_STG = SMEM_W + W_SLOTS * W_SLOT_BYTES;
-constexpr int SMEM_TOTAL = SMEM_STG + STG_BUF_BYTES;         // 216 KiB
+constexpr int SMEM_GRU = SMEM_STG + STG_BUF_BYTES;           // GRU operand landing zone: 4 x [128 rows][16 B] (W_hh h columns, state)
+constexpr int SMEM_TOTAL = SMEM_GRU + 4 * TILE_M * 16;       // 224 KiB
 constexpr int SMEM_DYNAMIC = SMEM_TOTAL + 3072;              // control block (3 KiB) in front; the whole 227 KiB of the SM
+static_assert(SMEM_DYNAMIC <= 227 * 1024, "shared memory of one SM");
 
 struct Bars {
     uint64_t fullA[A_SLOTS];       // activation chunk landed (expect_tx)
@@ -315,6 +317,41 @@ __device__ __forceinline__ void finalize_gru(const Frame& fr, int t, int m, int 
     *reinterpret_cast<float4*>(fr.h + (size_t)m * H + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
     if (fr.all_h)      // state entering frame t (bvrnn.py:205)
         *reinterpret_cast<float4*>(fr.all_h + ((size_t)m * fr.T + t) * H + u0) = make_float4(pf.b[12], pf.b[13], pf.b[14], pf.b[15]);
+}
+
+// GRU operands through cp.async (LDGSTS) instead of register loads: a load into registers that is still in flight holds up the
+// thread's later shared-memory / tensor-memory reads (1.2 us per GRU tile exposed, probe 131072 in
+// profiles/r02_recurrent_probes.txt), an asynchronous copy does not.  Landing zones, one 16-byte piece per row each:
+// the W_ih_z phi_z columns in the three staging quads a 48-wide exchange does not use (quad 3 of every sender), the
+// W_hh h columns and the state behind the staging buffer.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void prefetch_gru_async(const Op& op, const Frame& fr, int t, int m, int row, int col0, int u0,
+                                                   uint32_t stg, uint32_t zone) {
+    if (m < fr.M) {
+        const float* gi = op.addend + (size_t)t * op.add_tstride + (size_t)m * op.ldadd + col0;
+        const float* gh = fr.gh + (size_t)m * 3 * fr.H + col0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            cp_async16(stg + i * STG_SENDER_BYTES + 3 * 2048 + row * 16, gi + 4 * i);
+            cp_async16(zone + i * 2048 + row * 16, gh + 4 * i);
+        }
+        cp_async16(zone + 3 * 2048 + row * 16, fr.h + (size_t)m * fr.H + u0);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void collect_gru_async(const unsigned char* stg, const unsigned char* zone, int row, Prefetch& pf) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(stg + i * STG_SENDER_BYTES + 3 * 2048 + row * 16);
+        const float4 b = *reinterpret_cast<const float4*>(zone + i * 2048 + row * 16);
+        pf.a[4 * i] = a.x; pf.a[4 * i + 1] = a.y; pf.a[4 * i + 2] = a.z; pf.a[4 * i + 3] = a.w;
+        pf.b[4 * i] = b.x; pf.b[4 * i + 1] = b.y; pf.b[4 * i + 2] = b.z; pf.b[4 * i + 3] = b.w;
+    }
+    const float4 h = *reinterpret_cast<const float4*>(zone + 3 * 2048 + row * 16);
+    pf.b[12] = h.x; pf.b[13] = h.y; pf.b[14] = h.z; pf.b[15] = h.w;
 }
 
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
@@ -832,7 +869,11 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         // ---- 48-wide tile: thread = row, 12 columns = r, z, n of 4 hidden units ----
                         const int col0 = nt * 48 + 12 * rank, u0 = nt * 16 + 4 * rank;
                         Prefetch pf;
-                        if (hf == 0 && !(dbg_flags & 131072)) prefetch_epilogue(op, fr, t, m, col0, u0, pf);   // probe 131072 (wrong results): no GRU operand loads
+                        const bool gru_async = !(dbg_flags & 524288);       // 524288: the old register loads, for A/B timing
+                        if (hf == 0 && !(dbg_flags & 131072)) {             // probe 131072 (wrong results): no GRU operand loads
+                            if (gru_async) prefetch_gru_async(op, fr, t, m, row, col0, u0, stg_send, smem_base + SMEM_GRU);
+                            else prefetch_epilogue(op, fr, t, m, col0, u0, pf);
+                        }
                         if (!mbar_wait<false>(&bars.accFull[slot], full_parity, abort_flag, 31)) { dead = true; break; }
                         tc_fence_after();
                         const int sr = sIt;
@@ -857,11 +898,24 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         __syncwarp();
                         // one lane per peer: the three remote arrivals leave together instead of one after the other
                         if (lane < CLUSTER && lane != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)lane));
-                        if (hf == 0) finalize_gru(fr, t, m, row, m_tile, u0, v, pf);
+                        if (hf == 0) {
+                            if (gru_async && !(dbg_flags & 131072)) collect_gru_async(stg_recv, smem_gen + SMEM_GRU, row, pf);
+                            finalize_gru(fr, t, m, row, m_tile, u0, v, pf);
+                        }
+                        continue;
+                    }
+                    if ((dbg_flags & 262144) && op.kind == KIND_LINEAR && op.out_img == nullptr) {
+                        // timing probe (wrong results): the side products (dec.0_h h, W_hh h, W_ih_z phi_z) get no epilogue at all
+                        if (!mbar_wait<false>(&bars.accFull[slot], full_parity, abort_flag, 31)) { dead = true; break; }
+                        tc_fence_after();
+                        tc_fence_before();
+                        __syncwarp();
+                        release_acc();
                         continue;
                     }
                     // ---- 64-wide split tile (or 16-wide full-K tile): two threads per row, 8 columns each ----
                     const int col0 = pl.split ? nt * 64 + 16 * rank + 8 * hf : nt * 16 + 8 * hf;
+                    // (cp.async for these 8-column operands as well was measured and is much slower: 130.8 / 67 us per frame)
                     Prefetch8 pf;
                     prefetch8(op, fr, t, m, col0, pf);
                     if (!mbar_wait<false>(&bars.accFull[slot], full_parity, abort_flag, 31)) { dead = true; break; }
