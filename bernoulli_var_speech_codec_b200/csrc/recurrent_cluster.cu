@@ -670,7 +670,10 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     const Op& op = ctl.ops[e >> 8];
                     const int nt = (int)(e & 0xFF);
                     const int slot = wIt % W_SLOTS, round = wIt / W_SLOTS;
+                    BVC_TRACING(const bool probe_w = pl.n > 1 && j == pl.n - 1 && (i - j * nck) == 0;)
+                    BVC_TRACING(if (lane == 0 && probe_w) BVC_TRACE(24);)
                     if (round >= 1 && !mbar_wait<false>(&bars.emptyW[slot], (round - 1) & 1, abort_flag, 11)) { dead = true; return; }
+                    BVC_TRACING(if (lane == 0 && probe_w) BVC_TRACE(25);)
                     const uint32_t bytes = 2u * op.bn * 128u;
                     const unsigned char* src = op.w_img + ((size_t)nt * pl.k_chunks + pl.kc0 + c) * bytes;
                     if (elect_one()) {
@@ -681,6 +684,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         }
                     }
                     __syncwarp();
+                    BVC_TRACING(if (lane == 0 && probe_w) BVC_TRACE(26);)
                     ++wIt;
                 };
                 // weights do not depend on the previous phase: start them before waiting for it
@@ -768,7 +772,10 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             if (lane == 0 && c == nck - 1) BVC_TRACE(6);
                         }
                         const int ws = wIt % W_SLOTS, wr = wIt / W_SLOTS;
+                        BVC_TRACING(const bool probe_m = pl.n > 1 && j == pl.n - 1 && c == 0;)
+                        BVC_TRACING(if (lane == 0 && probe_m) BVC_TRACE(27);)
                         if (!mbar_wait<false>(&bars.fullW[ws], wr & 1, abort_flag, 23)) { dead = true; break; }
+                        BVC_TRACING(if (lane == 0 && probe_m) BVC_TRACE(28);)
                         ++wIt;
                         tc_fence_after();
                         if (elect_one()) {
@@ -796,6 +803,8 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             if (c == nck - 1) umma_commit(&bars.accFull[slot]);
                         }
                         __syncwarp();
+                        BVC_TRACING(if (lane == 0 && probe_m) BVC_TRACE(29);)
+                        BVC_TRACING(if (lane == 0 && pl.n > 1 && j == pl.n - 2 && c == 0) BVC_TRACE(30);)   // previous tile's chunk 0 issued
                     }
                     if (dead) break;
                 }

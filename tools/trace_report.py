@@ -34,9 +34,11 @@ if CLK:
         med = [np.nanmedian(fr[busy, ph, e] - ref) if e < n_ev else np.nan for _, e in ev]
         mx = [np.nanmax(fr[busy, ph, e] - ref) if e < n_ev else np.nan for _, e in ev]
         print("%3d  %4d  | " % (ph, int(busy.sum())) + " ".join("%6.0f" % v for v in med))
-        if n_ev > 27:
-            print("       MMA warp clk in: accEmpty waits %.0f, weight waits %.0f, issue regions %.0f, weight polls %.0f (median)" % tuple(
-                np.nanmedian(fr[busy, ph, e]) for e in (24, 25, 26, 27)))
+        if n_ev > 30 and not np.all(np.isnan(fr[busy, ph, 24])):
+            # weight ring probe on chunk 0 of the LAST tile of a multi-tile phase: copy warp 24 starts waiting for the slot, 25 slot
+            # free, 26 copy issued; MMA warp 30 previous tile's chunk 0 issued, 27 starts waiting for the chunk, 28 chunk landed, 29 its MMAs issued
+            print("       weight ring (last tile, chunk 0): prev chunk-0 MMAs issued %.0f | copy: wait slot %.0f, slot free %.0f, issued %.0f | MMA: wait %.0f, landed %.0f, issued %.0f" % tuple(
+                np.nanmedian(fr[busy, ph, e] - ref) for e in (30, 24, 25, 26, 27, 28, 29)))
         print("       max | " + " ".join("%6.0f" % v for v in mx))
     sys.exit(0)
 prev_done = np.nanmax(d[:, frame - 1, :, 13]) if frame > 0 else np.nanmin(fr[:, 0, 0])
