@@ -15,8 +15,10 @@ Synthetic random-init weights with the reference's checkpoint schema (the shippe
 One step of configs 1-3 = encode(x) followed by decode(codes, L) on one batch (two recurrences).
 
   value     device-resident: inputs already in HBM, CUDA-event timed, max over ranks
-  e2e       through the public facade with pinned HOST tensors: H2D of x, encode, D2H of codes, H2D of codes, decode,
-            D2H of audio, all inside the timed region
+  e2e       through the public API with pinned HOST tensors, every step's copies inside the timed region:
+            pipeline.HostPipeline (model.encode + model.decode per batch; the H2D of batch k+1 and the D2H of codes and
+            audio of batch k-1 run on the copy engines while batch k computes); `e2e.blocking` = the blocking facade calls
+            model.encode(x_cpu) -> codes_cpu -> model.decode(codes_cpu) with every copy exposed
   roofline  dominant kernel (recurrent_cluster_kernel, encode launch): algorithmic FLOPs / device time (CUDA events
             recorded inside the library around the launch) against the measured sustained bf16 peak; per-stage breakdown
   cpu_baseline / --impl reference   the reference's CPU path on the box's host cores, bounded sample, rank 0 only: the
@@ -461,9 +463,43 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = audio_s / float(e2e_s.item())
     codes_bytes = B * T * Z * 4
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (B * L * 4 + codes_bytes) * len(sweep),
+    e2e_blocking = {"value": e2e_value, "h2d_bytes_per_step": (B * L * 4 + codes_bytes) * len(sweep),
+                    "d2h_bytes_per_step": (codes_bytes + B * L * 4) * len(sweep),
+                    "api": "BVRNNCodecModel.encode(x_cpu_pinned, bitrate) -> codes_cpu; .decode(codes_cpu, L) -> wav_cpu (blocking calls)"}
+    # ---- the same through the host pipeline: every step still copies its audio in and its codes + audio out (pinned host
+    # buffers), but the copies of batch k + 1 / k - 1 run on the copy engines while batch k computes (pipeline.py) ----
+    from bernoulli_var_speech_codec_b200.pipeline import HostPipeline
+    pipe = HostPipeline(model, depth=2)
+    n_sub = args.steps * len(bitrates)
+
+    def run_pipeline(n):
+        tickets, last = [], None
+        for k in range(n):
+            tickets.append(pipe.submit(x_host, bitrates[k % len(bitrates)]))
+            if k >= 1:
+                last = pipe.result(tickets[k - 1])
+        last = pipe.result(tickets[n - 1])
+        return last
+
+    run_pipeline(max(2, min(args.warmup, 3)))
+    sync()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    t0.record()
+    pc_h, pw_h = run_pipeline(n_sub)
+    t1.record()
+    sync()
+    pipe_s = torch.tensor([max(time.perf_counter() - wall0, t0.elapsed_time(t1) / 1e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(pipe_s, op=dist.ReduceOp.MAX)
+    pipe.close()
+    pipe_ok = bool(torch.equal(pc_h, c_h) and torch.equal(pw_h, w_h))        # same outputs as the blocking calls
+    e2e = {"value": audio_s / float(pipe_s.item()), "unit": UNIT, "h2d_bytes_per_step": B * L * 4 * len(sweep),
            "d2h_bytes_per_step": (codes_bytes + B * L * 4) * len(sweep),
-           "api": "BVRNNCodecModel.encode(x_cpu_pinned, bitrate) -> codes_cpu; .decode(codes_cpu, L) -> wav_cpu"}
+           "api": "pipeline.HostPipeline(model).submit(x_cpu_pinned, bitrate) / .result() -> (codes_cpu, wav_cpu): "
+                  "BVRNNCodecModel.encode + .decode per batch, H2D of batch k+1 and D2H of batch k-1 overlapped with batch k",
+           "matches_blocking_calls": pipe_ok, "blocking": e2e_blocking}
 
     # ---- fused forward (a separate figure with its own flop count, never mixed into `value`) ----
     # model(x, bitrate) = decode(encode(x)) with ONE recurrence: the encoder's internal decoder output feeds the vocoder

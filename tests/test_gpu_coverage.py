@@ -399,3 +399,32 @@ def test_stream_session_matches_offline(model_var):
     w, v = sess.encode_step(x[:, :256])
     assert int(v[1]) == 0 and int(v[0]) == 1
     sess.close()
+
+
+@pytest.mark.gpu
+def test_host_pipeline_matches_blocking_calls(model_var):
+    """pipeline.HostPipeline: batches submitted back to back (copies of neighbouring batches overlapped with compute) give
+    exactly what the blocking host calls give, slot reuse included (4 batches through 2 slots)."""
+    from bernoulli_var_speech_codec_b200.pipeline import HostPipeline
+    L = 22050
+    xs = [_noise(3, L, 900 + i).pin_memory() for i in range(4)]
+    ref = []
+    for x in xs:
+        c = model_var.encode(x, 3000)
+        ref.append((c.clone(), model_var.decode(c, L).clone()))
+    pipe = HostPipeline(model_var, depth=2)
+    tickets, got = [], []
+    for k, x in enumerate(xs):
+        tickets.append(pipe.submit(x, 3000))
+        if k >= 1:
+            c, w = pipe.result(tickets[k - 1])
+            got.append((c.clone(), w.clone()))
+    c, w = pipe.result(tickets[-1])
+    got.append((c.clone(), w.clone()))
+    pipe.close()
+    for (rc, rw), (gc, gw) in zip(ref, got):
+        assert torch.equal(rc.cpu(), gc) and torch.equal(rw.cpu(), gw)
+    with pytest.raises(RuntimeError):
+        p2 = HostPipeline(model_var, depth=2)
+        for x in xs[:3]:
+            p2.submit(x, 3000)          # third submit without collecting the first
