@@ -702,6 +702,7 @@ struct UmmaStageArgs {
     const float* ieb[3][6];
     float* out[3];              // NCH = 3: out[0] = [B, n_out, C] mean of the resblocks; NCH = 1: out[chain] = its partial
     unsigned long long* trace;  // bring-up: CTA (0,0), tile 2: per job 4 %globaltimer stamps (+ 2 for the tile prologue)
+    int dbg;                    // BVC_VOC_DEBUG timing probes (wrong results): 1 no MMAs, 2 no weight copies, 4 no SnakeBeta / split maths
     UmmaStageWeights w;
 };
 
@@ -915,7 +916,9 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                 for (int s0 = 0; s0 < jb.steps; s0 += SPCW, ++it) {
                     const int slot = it % UM_WSLOTS, round = it / UM_WSLOTS;
                     if (round >= 1) um_wait(&w_empty[slot], (round - 1) & 1);
-                    if (um_elect()) {
+                    if (a.dbg & 2) {
+                        if (um_elect()) um_arrive(&w_full[slot]);
+                    } else if (um_elect()) {
                         const uint32_t bytes = (uint32_t)(min(SPCW, jb.steps - s0) * N * 64);
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(um_smem_u32(&w_full[slot])), "r"(bytes)
                                      : "memory");
@@ -992,8 +995,10 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                             for (int mt = 0; mt < MT; ++mt) {       // the weight step is fetched once per 128-row tile
                                 const uint64_t dah = dah0 + (uint64_t)(mt * UM_ROWS), dal = dah + a_lo16;
                                 const uint32_t dt = d_tmem + (uint32_t)(mt * L::tile_cols);
-                                um_mma(dt, dah, dwh, idesc2, first);
-                                um_mma(dt, dal, dwh, idesc, 1u);
+                                if (!(a.dbg & 1)) {
+                                    um_mma(dt, dah, dwh, idesc2, first);
+                                    um_mma(dt, dal, dwh, idesc, 1u);
+                                }
                             }
                             first = 1u;
                             dwh += (uint64_t)(N * 4);
@@ -1156,9 +1161,11 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                     restore(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, c2_off(c, K, l), K - 1);
                     tld(t_lane + c * 4 * N + 2 * N + CPT * ge, v);
                     epi_bar();
+                    if (!(a.dbg & 4)) {
 #pragma unroll
-                    for (int i = 0; i < CPT; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
-                    write_rows(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, v, c2_off(c, K, l), K - 1);
+                        for (int i = 0; i < CPT; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
+                        write_rows(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, v, c2_off(c, K, l), K - 1);
+                    }
                     publish(c);
                 } else {
                     // residual stream updated in TMEM: x_true = x + (sum of the second convs' biases so far)
@@ -1171,9 +1178,11 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                                                                                                            // during this one); first use per group
                     epi_bar();
                     if (l < 2) {
+                        if (!(a.dbg & 4)) {
 #pragma unroll
-                        for (int i = 0; i < CPT; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
-                        write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, v, c1_off(c, K, l + 1), ctx);
+                            for (int i = 0; i < CPT; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
+                            write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, v, c1_off(c, K, l + 1), ctx);
+                        }
                         publish(c);
                     } else {
 #pragma unroll
@@ -1660,6 +1669,7 @@ static int run_plain_stage(const VocoderWeights& w, int i, const StageIn& in, in
             }
             ua.w = w.umma[i];
             ua.trace = nullptr;
+            { static const int voc_dbg = getenv("BVC_VOC_DEBUG") ? atoi(getenv("BVC_VOC_DEBUG")) : 0; ua.dbg = voc_dbg; }
             static unsigned long long* trace_dev = nullptr;
             const bool tracing = getenv("BVC_VOC_TRACE") && atoi(getenv("BVC_VOC_TRACE")) == i;
             if (tracing) {
