@@ -428,3 +428,28 @@ def test_host_pipeline_matches_blocking_calls(model_var):
         p2 = HostPipeline(model_var, depth=2)
         for x in xs[:3]:
             p2.submit(x, 3000)          # third submit without collecting the first
+
+
+@pytest.mark.gpu
+def test_gru_operand_fetch_paths_agree(ckpts, cfg_var):
+    """The GRU epilogue fetches its operands (W_hh h, W_ih_z phi_z, state) with cp.async into shared-memory landing zones
+    that alias unused staging quads; BVC_REC_DEBUG=524288 selects the plain register loads.  Both must give bit-identical
+    codes and decoded mel (B = 300: three m-tiles, two of them full, ragged last one)."""
+    from bernoulli_var_speech_codec_b200 import BVRNNCodecModel
+    m = BVRNNCodecModel(cfg_var, *ckpts).eval()
+    x = _noise(300, 22050, 4242).to(m.device)
+    old = os.environ.get("BVC_REC_DEBUG")
+    try:
+        os.environ.pop("BVC_REC_DEBUG", None)
+        c0 = m.encode(x, 3000)
+        w0 = m.decode(c0, 22050)
+        os.environ["BVC_REC_DEBUG"] = "524288"
+        c1 = m.encode(x, 3000)
+        w1 = m.decode(c1, 22050)
+    finally:
+        if old is None:
+            os.environ.pop("BVC_REC_DEBUG", None)
+        else:
+            os.environ["BVC_REC_DEBUG"] = old
+    assert torch.equal(c0, c1)
+    assert torch.equal(w0, w1)
