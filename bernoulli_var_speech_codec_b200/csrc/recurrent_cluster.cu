@@ -234,6 +234,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // even the disabled checks cost ~4 % per frame in the latency-critical issue warp (measured A/B on one B200).
 // debug flag 64: stamps are the SM's clock64 (exact intervals inside one CTA) instead of %globaltimer (comparable across CTAs,
 // but it ticks in steps of ~0.26 us on this part)
+// Timing probes (BVC_REC_DEBUG bits; wrong results by construction) are compiled in only with -DBVC_REC_PROBES (or the tracing
+// build): like the disabled trace checks, run-time tests of the flag word in the issue / copy / epilogue loops are not free.
+#if defined(BVC_REC_PROBES) || defined(BVC_REC_TRACING)
+#define REC_DBG(bit) ((dbg_flags & (bit)) != 0)
+#else
+#define REC_DBG(bit) (false)
+#endif
 #ifdef BVC_REC_TRACING
 #define BVC_TRACE(ev)                                                                                             \
     do {                                                                                                          \
@@ -663,7 +670,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                 const int nck = pl.nck;
                 const int nW = pl.n * nck;
                 // experiment (debug flag 128): the CTAs that read the same activation quarter start at different chunks
-                const int rot = ((dbg_flags & 128) && nck == 4 && pl.n > 0) ? (int)(ctl.ent[pl.e_off] & 3) : 0;
+                const int rot = (REC_DBG(128) && nck == 4 && pl.n > 0) ? (int)(ctl.ent[pl.e_off] & 3) : 0;
                 auto issue_w = [&](int i) {
                     const int j = i / nck, c = ((i - j * nck) + rot) & (nck == 4 ? 3 : 0xFF);
                     const uint32_t e = ctl.ent[pl.e_off + j];
@@ -677,7 +684,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     const uint32_t bytes = 2u * op.bn * 128u;
                     const unsigned char* src = op.w_img + ((size_t)nt * pl.k_chunks + pl.kc0 + c) * bytes;
                     if (elect_one()) {
-                        if (dbg_flags & 4096) mbar_arrive(&bars.fullW[slot]);      // timing probe (wrong results): no weight copy
+                        if REC_DBG(4096) mbar_arrive(&bars.fullW[slot]);      // timing probe (wrong results): no weight copy
                         else {
                             mbar_expect_tx(&bars.fullW[slot], bytes);
                             bulk_g2s(smem_base + SMEM_W + slot * W_SLOT_BYTES, src, bytes, &bars.fullW[slot]);
@@ -712,7 +719,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             asm volatile("fence.proxy.async.global;\n" ::: "memory");
                             for (int c = 0; c < nck; ++c) {
                                 const int cs = nck == 4 ? ((c + rot) & 3) : c;
-                                if (dbg_flags & 32768) { mbar_arrive(&bars.fullA[c]); continue; }   // timing probe (wrong results): no activation copy
+                                if REC_DBG(32768) { mbar_arrive(&bars.fullA[c]); continue; }   // timing probe (wrong results): no activation copy
                                 mbar_expect_tx(&bars.fullA[c], ACT_CHUNK_BYTES);
                                 bulk_g2s(smem_base + SMEM_A + c * ACT_CHUNK_BYTES, src + (size_t)cs * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES,
                                          &bars.fullA[c]);
@@ -783,7 +790,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                             const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
                             const uint64_t dwh = descW + (uint64_t)((ws * W_SLOT_BYTES) >> 4);
                             const uint64_t dwl = dwh + (uint64_t)((bn * 128) >> 4);
-                            if (dbg_flags & 8192) {
+                            if REC_DBG(8192) {
                                 // timing probe (wrong results): no MMAs, only the commits
                             } else if (stacked) {
 #pragma unroll
@@ -878,8 +885,8 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         // ---- 48-wide tile: thread = row, 12 columns = r, z, n of 4 hidden units ----
                         const int col0 = nt * 48 + 12 * rank, u0 = nt * 16 + 4 * rank;
                         Prefetch pf;
-                        const bool gru_async = !(dbg_flags & 524288);       // 524288: the old register loads, for A/B timing
-                        if (hf == 0 && !(dbg_flags & 131072)) {             // probe 131072 (wrong results): no GRU operand loads
+                        const bool gru_async = !(dbg_flags & 524288);   // 524288 (always available): the old register loads, for the A/B test
+                        if (hf == 0 && !REC_DBG(131072)) {             // probe 131072 (wrong results): no GRU operand loads
                             if (gru_async) prefetch_gru_async(op, fr, t, m, row, col0, u0, stg_send, smem_base + SMEM_GRU);
                             else prefetch_epilogue(op, fr, t, m, col0, u0, pf);
                         }
@@ -908,12 +915,12 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                         // one lane per peer: the three remote arrivals leave together instead of one after the other
                         if (lane < CLUSTER && lane != rank) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&bars.stgEmpty), (uint32_t)lane));
                         if (hf == 0) {
-                            if (gru_async && !(dbg_flags & 131072)) collect_gru_async(stg_recv, smem_gen + SMEM_GRU, row, pf);
+                            if (gru_async && !REC_DBG(131072)) collect_gru_async(stg_recv, smem_gen + SMEM_GRU, row, pf);
                             finalize_gru(fr, t, m, row, m_tile, u0, v, pf);
                         }
                         continue;
                     }
-                    if ((dbg_flags & 262144) && op.kind == KIND_LINEAR && op.out_img == nullptr) {
+                    if (REC_DBG(262144) && op.kind == KIND_LINEAR && op.out_img == nullptr) {
                         // timing probe (wrong results): the side products (dec.0_h h, W_hh h, W_ih_z phi_z) get no epilogue at all
                         if (!mbar_wait<false>(&bars.accFull[slot], full_parity, abort_flag, 31)) { dead = true; break; }
                         tc_fence_after();
@@ -932,7 +939,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                     if (tid == 128 && j == pl.n - 1) BVC_TRACE(9);
                     tc_fence_after();
                     float v[8];
-                    if (pl.split && (dbg_flags & 2048)) {
+                    if (pl.split && REC_DBG(2048)) {
                         // timing probe (wrong results): no tensor-memory read, no reduce-scatter
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -995,7 +1002,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                               (trace && t < trace_frames && tid == 128 && j == pl.n - 1 && (dbg_flags & 64))
                                   ? trace + (((size_t)blockIdx.x * trace_frames + t) * MAX_PHASES + ph) * TRACE_EVENTS : nullptr);
 #else
-                    if (!(dbg_flags & 16384)) finalize8(op, fr, t, m, row, m_tile, col0, v, pf);   // probe 16384: no epilogue math / stores
+                    if (!REC_DBG(16384)) finalize8(op, fr, t, m, row, m_tile, col0, v, pf);   // probe 16384: no epilogue math / stores
 #endif
                 }
                 // ---- end of phase: publish this CTA's outputs to the m-tile's barrier domain ----
@@ -1004,7 +1011,7 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
                 // barrier (the CUTLASS semaphore pattern), and the consumer's copy thread issues fence.proxy.async after its
                 // acquire, before the bulk copies.  A writer-side fence.proxy.async here would be a MEMBAR.ALL.GPU in each of
                 // the epilogue threads on the critical path of every phase.
-                if (dbg_flags & 32) fence_proxy_async_all();
+                if REC_DBG(32) fence_proxy_async_all();
                 {   // barrier over the 8 epilogue warps; a failed wait anywhere retires all of them together
                     uint32_t any;
                     asm volatile(

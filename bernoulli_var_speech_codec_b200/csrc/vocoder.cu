@@ -702,10 +702,16 @@ struct UmmaStageArgs {
     const float* ieb[3][6];
     float* out[3];              // NCH = 3: out[0] = [B, n_out, C] mean of the resblocks; NCH = 1: out[chain] = its partial
     unsigned long long* trace;  // bring-up: CTA (0,0), tile 2: per job 4 %globaltimer stamps (+ 2 for the tile prologue)
-    int dbg;                    // BVC_VOC_DEBUG timing probes (wrong results): 1 no MMAs, 2 no weight copies, 4 no SnakeBeta / split maths
+    int dbg;                    // BVC_VOC_DEBUG timing probes (wrong results; only in builds with -DBVC_VOC_PROBES, the checks cost ~1 ms per
+                                // vocoder pass): 1 no MMAs, 2 no weight copies, 4 no SnakeBeta / split maths
     UmmaStageWeights w;
 };
 
+#ifdef BVC_VOC_PROBES
+#define UM_DBG(a, bit) ((a).dbg & (bit))
+#else
+#define UM_DBG(a, bit) 0
+#endif
 __device__ __forceinline__ uint32_t um_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ bool um_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -916,7 +922,7 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                 for (int s0 = 0; s0 < jb.steps; s0 += SPCW, ++it) {
                     const int slot = it % UM_WSLOTS, round = it / UM_WSLOTS;
                     if (round >= 1) um_wait(&w_empty[slot], (round - 1) & 1);
-                    if (a.dbg & 2) {
+                    if (UM_DBG(a, 2)) {
                         if (um_elect()) um_arrive(&w_full[slot]);
                     } else if (um_elect()) {
                         const uint32_t bytes = (uint32_t)(min(SPCW, jb.steps - s0) * N * 64);
@@ -995,7 +1001,7 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                             for (int mt = 0; mt < MT; ++mt) {       // the weight step is fetched once per 128-row tile
                                 const uint64_t dah = dah0 + (uint64_t)(mt * UM_ROWS), dal = dah + a_lo16;
                                 const uint32_t dt = d_tmem + (uint32_t)(mt * L::tile_cols);
-                                if (!(a.dbg & 1)) {
+                                if (!UM_DBG(a, 1)) {
                                     um_mma(dt, dah, dwh, idesc2, first);
                                     um_mma(dt, dal, dwh, idesc, 1u);
                                 }
@@ -1161,7 +1167,7 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                     restore(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, c2_off(c, K, l), K - 1);
                     tld(t_lane + c * 4 * N + 2 * N + CPT * ge, v);
                     epi_bar();
-                    if (!(a.dbg & 4)) {
+                    if (!UM_DBG(a, 4)) {
 #pragma unroll
                         for (int i = 0; i < CPT; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
                         write_rows(a2_off(c), (K - 1) + UM_TT + UM_PADR, K - 1, v, c2_off(c, K, l), K - 1);
@@ -1178,7 +1184,7 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                                                                                                            // during this one); first use per group
                     epi_bar();
                     if (l < 2) {
-                        if (!(a.dbg & 4)) {
+                        if (!UM_DBG(a, 4)) {
 #pragma unroll
                             for (int i = 0; i < CPT; ++i) v[i] = snake_fast(v[i] + pa[i], ea[i], ieb[i]);
                             write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, v, c1_off(c, K, l + 1), ctx);
