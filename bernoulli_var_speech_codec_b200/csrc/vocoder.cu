@@ -738,10 +738,16 @@ __device__ __forceinline__ unsigned long long um_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(v));
     return v;
 }
+// job timeline of one tile (BVC_VOC_TRACE=<file>): compiled in only with -DBVC_VOC_TRACING, the run-time checks sit in the
+// MMA-issue and epilogue loops of every job
+#ifdef BVC_VOC_TRACING
 #define UM_TRACE(slot)                                                                         \
     do {                                                                                       \
         if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile == 2) a.trace[slot] = um_ns(); \
     } while (0)
+#else
+#define UM_TRACE(slot) do { } while (0)
+#endif
 __device__ __forceinline__ void um_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(um_smem_u32(bar)) : "memory");
 }
