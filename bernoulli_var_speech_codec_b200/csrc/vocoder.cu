@@ -670,7 +670,8 @@ struct UmLayout {
     __host__ __device__ static constexpr int c2(int c) { return c == 0 ? c1(NCH) : c2(c - 1) + 2 * G * (um_K(c - 1) - 1) * 3 * 16; }
     static constexpr int wring = (c2(NCH) + 1023) / 1024 * 1024;
     static constexpr int x0 = wring + UM_WSLOTS * UM_WSLOT_BYTES;          // fp32 [TT][C + 4]: the upsampled tile (bulk-copied)
-    static constexpr int total = x0 + TT * (C + 4) * 4;
+    static constexpr int cst = x0 + TT * (C + 4) * 4;                      // per-channel constants of the jobs: [chain][20][C] fp32
+    static constexpr int total = cst + NCH * 20 * C * 4;
     // TMEM columns per 128-row tile and chain: [x | x aux | D1 | D1 aux], N each.  A product is a_hi [w_hi | w_lo] (one MMA
     // of width 2 N: main and aux accumulator) + a_lo w_hi (width N): the activation operand, whose fetch from shared
     // memory bounds these narrow MMAs, is read twice per k16 step instead of three times; the epilogue adds main + aux.
@@ -890,6 +891,25 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
 
     // zero everything once: causal zero history, and the pad rows that zero-weight taps may touch must be finite
     for (int i = tid; i < L::wring / 16; i += UM_THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    // Per-channel constants (biases, SnakeBeta exp(alpha), 1 / exp(beta)) of every job, once per CTA: vector v of chain c at
+    // cst[(c * 20 + v) * C].  v = 0, 1: first activation; 2 + 6 l + {0, 1, 2}: bias / ea / ieb behind the dilated conv of
+    // layer l; 2 + 6 l + {3, 4, 5}: bias sum / ea / ieb behind its second conv.  Read with ld.shared in the job loop: a
+    // global load in flight would hold up the epilogue's next shared- and tensor-memory reads.
+    {
+        float* cst = reinterpret_cast<float*>(sm + L::cst);
+        for (int i = tid; i < NCH * 20 * C; i += UM_THREADS) {
+            const int c = i / (20 * C), r = i - c * 20 * C, v = r / C, ch = r - v * C, kc = kc0 + c;
+            const float* src = nullptr;
+            if (v == 0) src = a.ea[kc][0];
+            else if (v == 1) src = a.ieb[kc][0];
+            else {
+                const int l = (v - 2) / 6, w = (v - 2) % 6;
+                src = w == 0 ? a.w.b1[kc][l] : w == 1 ? a.ea[kc][2 * l + 1] : w == 2 ? a.ieb[kc][2 * l + 1]
+                    : w == 3 ? a.w.bsum[kc][l] : l < 2 ? (w == 4 ? a.ea[kc][2 * (l + 1)] : a.ieb[kc][2 * (l + 1)]) : nullptr;
+            }
+            cst[i] = src ? __ldg(src + ch) : 0.f;
+        }
+    }
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(um_smem_u32(&a_ready[i])), "r"(4 * GE * MT));   // the owning group's warps
@@ -1074,10 +1094,11 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
             __syncwarp();
             if (lane == 0) um_arrive(&a_ready[c]);
         };
-        auto loadc = [&](const float* ptr, float* o) {      // this thread's CPT per-channel constants
+        const float* cst = reinterpret_cast<const float*>(sm + L::cst);
+        auto loadc = [&](int c, int v, float* o) {          // this thread's CPT per-channel constants (vector v of chain c)
 #pragma unroll
             for (int q = 0; q < CPT / 4; ++q) {
-                const float4 u = __ldg(reinterpret_cast<const float4*>(ptr + CPT * ge) + q);
+                const float4 u = *(reinterpret_cast<const float4*>(cst + (c * 20 + v) * C + CPT * ge) + q);
                 o[4 * q] = u.x; o[4 * q + 1] = u.y; o[4 * q + 2] = u.z; o[4 * q + 3] = u.w;
             }
         };
@@ -1117,8 +1138,8 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                 um_st8(t_lane + c * 4 * N + N + CPT * ge + 8 * s8, zero8);      // the second convs accumulate onto [x | 0]
             }
             float ea[CPT], ieb[CPT], y[CPT];
-            loadc(a.ea[kc][0], ea);
-            loadc(a.ieb[kc][0], ieb);
+            loadc(c, 0, ea);
+            loadc(c, 1, ieb);
 #pragma unroll
             for (int i = 0; i < CPT; ++i) y[i] = snake_fast(xr[i], ea[i], ieb[i]);
             write_rows(a1_off(c), (K - 1) * 5 + UM_TT + UM_PADR, (K - 1) * 5, y, c1_off(c, K, 0), (K - 1) * 1);
@@ -1159,10 +1180,10 @@ __global__ void __launch_bounds__(UmLayout<C, U, MT, NCH>::threads, 1) stage_umm
                 float v[CPT], pa[CPT], ea[CPT], ieb[CPT];
                 // per-channel constants of this job are fetched while the MMAs are still running
                 if (!jb.conv2) {
-                    loadc(a.w.b1[kc][l], pa); loadc(a.ea[kc][2 * l + 1], ea); loadc(a.ieb[kc][2 * l + 1], ieb);
+                    loadc(c, 2 + 6 * l, pa); loadc(c, 3 + 6 * l, ea); loadc(c, 4 + 6 * l, ieb);
                 } else {
-                    loadc(a.w.bsum[kc][l], pa);
-                    if (l < 2) { loadc(a.ea[kc][2 * (l + 1)], ea); loadc(a.ieb[kc][2 * (l + 1)], ieb); }
+                    loadc(c, 5 + 6 * l, pa);
+                    if (l < 2) { loadc(c, 6 + 6 * l, ea); loadc(c, 7 + 6 * l, ieb); }
                 }
                 um_wait(&d_ready[c], d_seen[c] & 1);
                 ++d_seen[c];
