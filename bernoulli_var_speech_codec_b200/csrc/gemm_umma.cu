@@ -27,6 +27,7 @@ using rec::ACT_PART_BYTES;
 
 constexpr int kThreads = 256;
 constexpr int TILE_N = 256;
+static_assert(kThreads == TILE_N, "one thread stages one bias value");
 constexpr int W_PART_BYTES = TILE_N * 128;
 constexpr int W_CHUNK_BYTES = 2 * W_PART_BYTES;
 constexpr int STAGE_BYTES = ACT_CHUNK_BYTES + W_CHUNK_BYTES;     // 96 KiB
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], acc_bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float bias_s[TILE_N];       // the tile's bias: no global load between two tensor-memory reads of the epilogue
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(GemmArgs a) {
     const size_t m_tile = blockIdx.y;
     const int KC = a.k_chunks;
 
+    bias_s[tid] = a.bias ? __ldg(a.bias + n_tile * TILE_N + tid) : 0.f;      // kThreads == TILE_N
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(&acc_bar, 1);
@@ -213,10 +216,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(GemmArgs a) {
             float v[16];
             tmem_ld16(taddr + c0, v);
             const int col0 = n_tile * TILE_N + c0;
-            if (a.bias) {
+            {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col0) + i);
+                    const float4 b = *(reinterpret_cast<const float4*>(bias_s + c0) + i);
                     v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
                 }
             }
