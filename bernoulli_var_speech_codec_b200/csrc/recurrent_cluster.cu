@@ -562,7 +562,7 @@ __device__ __forceinline__ void reduce_parts8(const float* own, int rank, int hf
 
 // Per-CTA schedule, built once in shared memory so that no role chases pointers through L2 inside the time loop
 // (the cluster- and gpu-scope fences of the protocol invalidate L1 all the time).
-constexpr int MAX_MY_ENTRIES = 320;
+constexpr int MAX_MY_ENTRIES = 256;       // <= 193 tiles per CTA and frame at 16 m-tiles on 32 clusters (bvrnn.cu: persistent_max_rows)
 struct PhaseLocal {
     const unsigned char* a_src;    // first activation chunk of this CTA (m-tile and K quarter applied)
     int nck;                       // activation / weight chunks per entry for this CTA
@@ -576,6 +576,8 @@ struct Control {
     Bars bars;
     uint32_t tmem_slot;
     uint32_t n_ops;
+    Frame frame;                          // per-call constants: read from shared memory in the loops (a global load in flight
+                                          // holds up the thread's later shared- / tensor-memory reads)
     Op ops[MAX_OPS];
     PhaseLocal ph[MAX_PHASES];
     unsigned short ent[MAX_MY_ENTRIES];   // (op << 8) | n_tile
@@ -597,8 +599,10 @@ recurrent_cluster_kernel(const Program* __restrict__ prog, unsigned* sync_words)
     const uint32_t smem_base = smem_u32(smem_dyn) + CONTROL_BYTES;
     unsigned char* smem_gen = smem_dyn + CONTROL_BYTES;
 
-    const Frame& fr = prog->frame;
-    const int T = fr.T, n_phases = prog->n_phases;
+    for (int i = tid; i < (int)(sizeof(Frame) / 4); i += kThreads)
+        reinterpret_cast<uint32_t*>(&ctl.frame)[i] = reinterpret_cast<const uint32_t*>(&prog->frame)[i];
+    const Frame& fr = ctl.frame;          // valid after the __syncthreads below; T / n_phases are taken from global memory here
+    const int T = prog->frame.T, n_phases = prog->n_phases;
     const int m_tile = prog->cluster_mtile[cluster];
     const unsigned dom_ctas = (unsigned)prog->mtile_ctas[m_tile];
     unsigned* counter = sync_words + 32 * (1 + m_tile);
