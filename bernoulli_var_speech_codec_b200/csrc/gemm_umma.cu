@@ -5,14 +5,13 @@
 // ready-made shared-memory images the persistent recurrent kernel uses (recurrent.cuh: 64-wide K chunks, split bf16
 // hi + lo, SWIZZLE_128B), so a chain of layers never leaves that format: the epilogue of one GEMM writes the
 // activation images the next one bulk-copies.
-//   tile       128 rows x 256 columns per CTA, K streamed in 64-wide chunks: 32 KiB of activations + 64 KiB of weights
-//              per stage, 2 stages (the kernel is bound by L2 -> SM operand traffic, both stages are always in flight)
+//   tile       128 rows x 256 columns, K streamed in 64-wide chunks: 32 KiB of activations + 64 KiB of weights per stage,
+//              2 stages; PERSISTENT: one CTA per SM walks the tiles (n fastest: the CTAs that share an activation tile run
+//              together and it is read from HBM once), two TMEM accumulators of 256 columns
 //   roles      warp 1: cp.async.bulk producer; warp 0: tcgen05.mma issuer (M = 128, N = 256, three MMAs per k16 step for
-//              the split-bf16 product); warps 4-7: TMEM -> registers -> bias / ELU -> output
-//   output     activation images for the next layer, or fp32 rows staged through the (then idle) pipeline buffers so
-//              that the global stores are coalesced
-// blockIdx.x walks the n-tiles of one m-tile, so the CTAs that share an activation tile run together and it is read
-// from HBM once.
+//              the split-bf16 product); warps 4-7: TMEM -> registers -> bias / ELU -> output of tile i under the main loop
+//              of tile i + 1
+//   output     activation images for the next layer, or fp32 rows (a thread writes 64 contiguous bytes of its row per step)
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -32,9 +31,7 @@ constexpr int W_PART_BYTES = TILE_N * 128;
 constexpr int W_CHUNK_BYTES = 2 * W_PART_BYTES;
 constexpr int STAGE_BYTES = ACT_CHUNK_BYTES + W_CHUNK_BYTES;     // 96 KiB
 constexpr int STAGES = 2;
-constexpr int OUT_PITCH = TILE_N + 4;                            // floats per staged output row
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
-static_assert(128 * OUT_PITCH * 4 <= STAGES * STAGE_BYTES, "fp32 output staging reuses the pipeline buffers");
 
 struct GemmArgs {
     const unsigned char* a_img;    // [m_tiles][k_chunks] activation images
@@ -43,6 +40,7 @@ struct GemmArgs {
     float* out_f;                  // fp32 [M][ldo] or null
     unsigned char* out_img;        // [m_tiles][out_kchunks] or null
     int k_chunks, out_kchunks, ldo, M, N, act;
+    int n_tiles_n, total_tiles;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,27 +135,28 @@ __device__ __forceinline__ void store_img16(unsigned char* img, size_t m_tile, i
     *reinterpret_cast<uint4*>(base + ACT_PART_BYTES + p1) = l1;
 }
 
+// Persistent: one CTA per SM walks the tiles (n fastest, so the CTAs that share an activation tile run together); two TMEM
+// accumulators, so the epilogue of tile i (tensor memory -> bias / ELU -> images or fp32 rows) runs under the main loop of
+// tile i + 1, and TMEM allocation, barrier set-up and the first-chunk latency are paid once per CTA instead of once per
+// tile (the one-tile-per-CTA version spent ~35 % of a tile outside the MMAs).
 __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], acc_bar;
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float bias_s[TILE_N];       // the tile's bias: no global load between two tensor-memory reads of the epilogue
+    __shared__ __align__(16) float bias_s[2][TILE_N];    // per accumulator: the tile's bias (no global load between two TMEM reads)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    unsigned char* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
-    const int n_tile = blockIdx.x;
-    const size_t m_tile = blockIdx.y;
     const int KC = a.k_chunks;
+    const int n_tiles_n = a.n_tiles_n, total = a.total_tiles;
 
-    bias_s[tid] = a.bias ? __ldg(a.bias + n_tile * TILE_N + tid) : 0.f;      // kThreads == TILE_N
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(&acc_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)),
-                     "r"((uint32_t)TILE_N));
+                     "r"((uint32_t)(2 * TILE_N)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
     }
     tc_fence_before();
@@ -167,14 +166,20 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(GemmArgs a) {
 
     if (warp == 1) {
         if (lane == 0) {
-            const unsigned char* a_src = a.a_img + m_tile * KC * ACT_CHUNK_BYTES;
-            const unsigned char* w_src = a.w_img + (size_t)n_tile * KC * W_CHUNK_BYTES;
-            for (int kc = 0; kc < KC; ++kc) {
-                const int s = kc % STAGES, round = kc / STAGES;
-                if (round >= 1) mbar_wait(&empty[s], (round - 1) & 1);
-                mbar_expect_tx(&full[s], STAGE_BYTES);
-                bulk_g2s(smem_base + s * STAGE_BYTES, a_src + (size_t)kc * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES, &full[s]);
-                bulk_g2s(smem_base + s * STAGE_BYTES + ACT_CHUNK_BYTES, w_src + (size_t)kc * W_CHUNK_BYTES, W_CHUNK_BYTES, &full[s]);
+            uint32_t kcnt = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const size_t m_tile = (size_t)(tile / n_tiles_n);
+                const int n_tile = tile % n_tiles_n;
+                const unsigned char* a_src = a.a_img + m_tile * KC * ACT_CHUNK_BYTES;
+                const unsigned char* w_src = a.w_img + (size_t)n_tile * KC * W_CHUNK_BYTES;
+                for (int kc = 0; kc < KC; ++kc, ++kcnt) {
+                    const int s = kcnt % STAGES;
+                    const uint32_t round = kcnt / STAGES;
+                    if (round >= 1) mbar_wait(&empty[s], (round - 1) & 1);
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    bulk_g2s(smem_base + s * STAGE_BYTES, a_src + (size_t)kc * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES, &full[s]);
+                    bulk_g2s(smem_base + s * STAGE_BYTES + ACT_CHUNK_BYTES, w_src + (size_t)kc * W_CHUNK_BYTES, W_CHUNK_BYTES, &full[s]);
+                }
             }
         }
         __syncwarp();
@@ -182,78 +187,81 @@ __global__ void __launch_bounds__(kThreads, 1) linear_umma_kernel(GemmArgs a) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(128, TILE_N);
             const uint64_t d0 = make_desc(smem_base);
-            for (int kc = 0; kc < KC; ++kc) {
-                const int s = kc % STAGES, round = kc / STAGES;
-                mbar_wait(&full[s], round & 1);
+            uint32_t kcnt = 0, tcnt = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcnt) {
+                const uint32_t acc = tcnt & 1u;
+                if (tcnt >= 2) mbar_wait(&acc_empty[acc], ((tcnt >> 1) - 1) & 1);     // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t dah = d0 + (uint64_t)((s * STAGE_BYTES) >> 4);
-                const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
-                const uint64_t dwh = dah + (ACT_CHUNK_BYTES >> 4);
-                const uint64_t dwl = dwh + (W_PART_BYTES >> 4);
+                const uint32_t d_tmem = tmem + acc * TILE_N;
+                for (int kc = 0; kc < KC; ++kc, ++kcnt) {
+                    const int s = kcnt % STAGES;
+                    mbar_wait(&full[s], (kcnt / STAGES) & 1);
+                    tc_fence_after();
+                    const uint64_t dah = d0 + (uint64_t)((s * STAGE_BYTES) >> 4);
+                    const uint64_t dal = dah + (ACT_PART_BYTES >> 4);
+                    const uint64_t dwh = dah + (ACT_CHUNK_BYTES >> 4);
+                    const uint64_t dwl = dwh + (W_PART_BYTES >> 4);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {   // small terms first
-                    umma(tmem, dal + 2 * ks, dwh + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
-                    umma(tmem, dah + 2 * ks, dwl + 2 * ks, idesc, 1u);
-                    umma(tmem, dah + 2 * ks, dwh + 2 * ks, idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {   // small terms first
+                        umma(d_tmem, dal + 2 * ks, dwh + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
+                        umma(d_tmem, dah + 2 * ks, dwl + 2 * ks, idesc, 1u);
+                        umma(d_tmem, dah + 2 * ks, dwh + 2 * ks, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
                 }
-                umma_commit(&empty[s]);
+                umma_commit(&acc_full[acc]);
             }
-            umma_commit(&acc_bar);
         }
         __syncwarp();
-    }
-
-    // ---- epilogue: warps 4-7 own one accumulator row each ----
-    float* stage_f = reinterpret_cast<float*>(smem_gen);     // fp32 output staging (pipeline buffers are idle by then)
-    if (warp >= 4) {
-        mbar_wait(&acc_bar, 0);
-        tc_fence_after();
-        const int quad = warp & 3, row = quad * 32 + lane;
-        const size_t m = m_tile * 128 + row;
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16);
+    } else if (warp >= 4) {
+        // ---- epilogue: warps 4-7 own one accumulator row each ----
+        const int quad = warp & 3, row = quad * 32 + lane, et = tid - 128;
+        uint32_t tcnt = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcnt) {
+            const size_t m_tile = (size_t)(tile / n_tiles_n);
+            const int n_tile = tile % n_tiles_n;
+            const uint32_t acc = tcnt & 1u;
+            bias_s[acc][et] = a.bias ? __ldg(a.bias + n_tile * TILE_N + et) : 0.f;
+            bias_s[acc][et + 128] = a.bias ? __ldg(a.bias + n_tile * TILE_N + et + 128) : 0.f;
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            mbar_wait(&acc_full[acc], (tcnt >> 1) & 1);
+            tc_fence_after();
+            const size_t m = m_tile * 128 + row;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * TILE_N;
 #pragma unroll 1
-        for (int c0 = 0; c0 < TILE_N; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);
-            const int col0 = n_tile * TILE_N + c0;
-            {
+            for (int c0 = 0; c0 < TILE_N; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                const int col0 = n_tile * TILE_N + c0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 b = *(reinterpret_cast<const float4*>(bias_s + c0) + i);
+                    const float4 b = *(reinterpret_cast<const float4*>(&bias_s[acc][c0]) + i);
                     v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
                 }
-            }
-            if (a.act == 1) {
+                if (a.act == 1) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
-            } else if (a.act == 2) {      // Bernoulli probabilities of the prior head (bvrnn.py:68-73)
+                    for (int i = 0; i < 16; ++i) v[i] = elu_fast(v[i]);
+                } else if (a.act == 2) {      // Bernoulli probabilities of the prior head (bvrnn.py:68-73)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = sigmoidf_(v[i]);
-            }
-            if (a.out_img && col0 < a.N) store_img16(a.out_img, m_tile, a.out_kchunks, row, col0, v);
-            if (a.out_f) {
+                    for (int i = 0; i < 16; ++i) v[i] = sigmoidf_(v[i]);
+                }
+                if (a.out_img && col0 < a.N) store_img16(a.out_img, m_tile, a.out_kchunks, row, col0, v);
+                if (a.out_f && m < (size_t)a.M && col0 < a.N) {      // 64 contiguous bytes of the row: two full sectors
+                    float4* dst = reinterpret_cast<float4*>(a.out_f + m * a.ldo + col0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    *reinterpret_cast<float4*>(stage_f + row * OUT_PITCH + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
             }
-        }
-        (void)m;
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (a.out_f) {   // coalesced fp32 rows: a warp writes 512 contiguous bytes of one row per instruction
-        const int n0 = n_tile * TILE_N;
-        for (int i = tid; i < 128 * (TILE_N / 4); i += kThreads) {
-            const int r = i / (TILE_N / 4), c4 = i % (TILE_N / 4);
-            const size_t m = m_tile * 128 + r;
-            if (m < (size_t)a.M && n0 + c4 * 4 < a.N)
-                *reinterpret_cast<float4*>(a.out_f + m * a.ldo + n0 + c4 * 4) =
-                    *reinterpret_cast<const float4*>(stage_f + r * OUT_PITCH + c4 * 4);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&acc_empty[acc])) : "memory");
+            }
         }
     }
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((uint32_t)TILE_N));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((uint32_t)(2 * TILE_N)));
     }
 }
 
@@ -307,7 +315,16 @@ int linear_umma(const unsigned char* a_img, int M, const WImg& w, const float* b
     a.k_chunks = (w.K + 63) / 64;
     a.out_kchunks = (w.N + 63) / 64;
     a.ldo = ldo; a.M = M; a.N = w.N; a.act = act;
-    dim3 grid((w.N + TILE_N - 1) / TILE_N, (M + 127) / 128);
+    a.n_tiles_n = (w.N + TILE_N - 1) / TILE_N;
+    a.total_tiles = a.n_tiles_n * ((M + 127) / 128);
+    static int sms_of[kMaxDevices] = {};
+    if (!sms_of[dslot]) {
+        int dev = 0, n = 0;
+        BVC_CUDA(cudaGetDevice(&dev));
+        BVC_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        sms_of[dslot] = n;
+    }
+    const int grid = a.total_tiles < sms_of[dslot] ? a.total_tiles : sms_of[dslot];
     linear_umma_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(a);
     BVC_CHECK_LAUNCH();
     return BVC_OK;
